@@ -1,0 +1,272 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the SRCNN hot path (ProcessSRCNN: colour-in -> resize -> fused conv I/II/III -> colour-out).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c4|c5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one synthetic frame per GPU (BASELINE.json configs[1]: 1920x1080 RGB x2.0
+bicubic -> 3840x2160).  Frames are independent units, so N GPUs process N frames per step with no collective
+(weak scaling); torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the timing.
+
+Printed JSON (one line, rank 0):
+  value     whole-job output megapixels/s, inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps
+  e2e       same metric through the C-ABI call srcnn_b200_pass_host with pinned HOST buffers (H2D + kernels + D2H)
+  roofline  the fused-conv kernel: algorithmic 16 064 flop per output pixel / its CUDA-event duration, against the
+            measured dense bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own CPU code (oracle/_ref, OpenMP, all host cores) on a bounded sample of the workload
+`--impl reference` times that CPU implementation alone and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+FLOP_PER_PX = 16064            # conv I 81*64 + conv II 64*32 + conv III 25*32 MACs, x2
+WORKLOADS = {
+    # name: (h, w, d, multiply, filter, description)
+    "c2": (1080, 1920, 3, 2.0, 2, "synthetic 1920x1080 RGB x2.0 bicubic -> 3840x2160 (BASELINE configs[1])"),
+    "c4": (512, 512, 3, 2.0, 3, "synthetic 512x512 RGB x2.0 Lanczos-3 -> 1024x1024 (one frame of BASELINE configs[3])"),
+    "c5": (2160, 3840, 3, 1.5, 4, "synthetic 3840x2160 RGB x1.5 B-spline -> 5760x3240, conv-output on (BASELINE configs[4])"),
+}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return dict(tf=float(j["bf16_tflops"]), hbm=float(j["hbm_gbs"]), src="measured (MEASURED_PEAKS.json, burst bf16)")
+    return dict(tf=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 6] or [r for (_, r) in self.rows if len(r) >= 6]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+def cpu_reference_run(h, w, d, m, filt, conv_on, budget_s=12.0):
+    """the reference's CPU implementation (oracle/_ref; the plain-C port if the reference was not compiled) on a
+    bounded sample: a horizontal crop of the workload frame sized for a few seconds of CPU work"""
+    import oracle_lib as O
+    orc = O.best()
+    sh = min(h, max(64, (270 * 1920) // max(w, 1)))            # ~0.5 M source px
+    img = O.synth("uniform", sh, w, d, 42)
+    ow, oh = O.out_dims(w, sh, m)
+    t0 = time.perf_counter(); rc, out, _ = orc.process(img, m, filt, False, conv_on); dt = time.perf_counter() - t0
+    assert rc == 0
+    runs, best = 1, dt
+    while runs < 3 and (time.perf_counter() - t0) + best < budget_s:
+        t1 = time.perf_counter(); orc.process(img, m, filt, False, conv_on); best = min(best, time.perf_counter() - t1); runs += 1
+    return dict(value=ow * oh / best / 1e6, unit="output MP/s", cores=orc.threads,
+                kind="reference" if orc.kind == "reference" else "port",
+                sample="%dx%dx%d crop of the workload frame -> %dx%d, best of %d run(s), %.2f s each, OpenMP threads=%d"
+                       % (w, sh, d, ow, oh, runs, best, orc.threads)), best, ow * oh
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    h, w, d, m, filt, desc = wl
+    conv_on = args.workload == "c5"
+    vals = []
+    for i in range(args.warmup + args.steps):
+        cb, dt, px = cpu_reference_run(h, w, d, m, filt, conv_on, budget_s=0.0)
+        if i >= args.warmup:
+            vals.append((cb, dt))
+    cb = vals[0][0]
+    tot = sum(dt for _, dt in vals)
+    v = px * len(vals) / tot / 1e6
+    cb["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": "output MP/s, SRCNN x2 to 4K (ProcessSRCNN hot path)", "value": v, "unit": "output MP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(vals) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "sample": cb["sample"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "output MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--conv", default="tensor", choices=["tensor", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import libsrcnn_b200 as S
+    import oracle_lib as O
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    h, w, d, m, filt, desc = wl
+    conv_on = args.workload == "c5"
+    ow, oh = S.output_dims(w, h, m)
+    out_px = ow * oh
+    ctx = S.Context(local, S.CONV_TENSOR if args.conv == "tensor" else S.CONV_EXACT)
+    img = O.synth("uniform", h, w, d, 42 + rank)
+    d_src = torch.from_numpy(img).cuda()
+    d_out = torch.empty((oh, ow, d), dtype=torch.uint8, device="cuda")
+    d_conv = torch.empty((oh, ow), dtype=torch.uint8, device="cuda") if conv_on else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    def step():
+        ctx.pass_device(d_src.data_ptr(), w, h, d, m, filt, d_out.data_ptr(), d_conv.data_ptr() if conv_on else 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+
+    # ---- timed region: K steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps
+    ctx.set_timing(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    conv_ms, stage_ms = [], []
+    launches0 = ctx.launches
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    for i in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(i & 0xff)                                          # evict the previous step's lines from L2
+        ev[i][0].record(stream)
+        step()
+        ev[i][1].record(stream)
+        ctx.sync()                                                         # also collects the per-kernel events
+        t = ctx.timings(); conv_ms.append(t["conv"]); stage_ms.append(t)
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    launches = ctx.launches - launches0
+    ctx.set_timing(False)
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    value = out_px * world * args.steps / (total_ms_max * 1e-3) / 1e6
+
+    # ---- end to end: the C-ABI call with pinned host buffers (H2D + kernels + D2H inside the timed region)
+    h_src = S.pinned_empty((h, w, d)); h_src[...] = img
+    h_out = S.pinned_empty((oh, ow, d)); h_conv = S.pinned_empty((oh, ow)) if conv_on else None
+    for _ in range(2):
+        ctx.pass_host(h_src, m, filt, conv_on, out=h_out, conv=h_conv)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.pass_host(h_src, m, filt, conv_on, out=h_out, conv=h_conv)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = out_px * world * args.steps / float(te.item()) / 1e6
+    # the drop-in C++ call itself (pageable new[] output), rank 0, for reference
+    dropin = None
+    if rank == 0:
+        S.process_srcnn(img, m, filt, False, conv_on)
+        t0 = time.perf_counter(); n = max(3, args.steps // 4)
+        for _ in range(n):
+            rc, _, _ = S.process_srcnn(img, m, filt, False, conv_on)
+        dropin = out_px * n / (time.perf_counter() - t0) / 1e6 if rc == 0 else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    conv_avg_ms = float(np.mean(conv_ms))
+    achieved_tf = out_px * FLOP_PER_PX / (conv_avg_ms * 1e-3) / 1e12
+    stage_avg = {k: float(np.mean([s[k] for s in stage_ms])) for k in stage_ms[0]}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu, _, _ = cpu_reference_run(h, w, d, m, filt, conv_on)
+    line = {
+        "metric": "output MP/s, SRCNN x2 to 4K (ProcessSRCNN hot path)", "value": value, "unit": "output MP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate (conv), f64 (resize), f32 (colour)" if args.conv == "tensor" else "f32 (conv exact mode), f64 (resize)",
+        "data": "synthetic",
+        "config": {"workload": desc, "frames_per_step": world, "sharding": "one frame per GPU, no collective",
+                   "conv_mode": args.conv, "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                   "conv_output": conv_on},
+        "e2e": {"value": e2e_val, "unit": "output MP/s", "h2d_bytes_per_step": int(img.nbytes) * world,
+                "d2h_bytes_per_step": (out_px * d + (out_px if conv_on else 0)) * world,
+                "api": "srcnn_b200_pass_host (C-ABI, pinned host buffers)", "dropin_ProcessSRCNN_pageable": dropin},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "fused conv I+II+III (%s)" % args.conv, "bound": "tensor", "achieved": achieved_tf,
+                     "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf"], "traffic": None,
+                     "peak_source": pk["src"], "kernel_ms": conv_avg_ms,
+                     "algorithmic_flop_per_launch": out_px * FLOP_PER_PX},
+        "stage_ms": stage_avg,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

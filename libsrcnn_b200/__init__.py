@@ -1,0 +1,270 @@
+"""libsrcnn_b200 -- Python (ctypes) binding of the B200-native SRCNN library.
+
+The product is the shared library ``libsrcnn_b200/lib/libsrcnn.so`` (C++ drop-in API ``ProcessSRCNN`` /
+``ConfigureFilterSRCNN`` + the ``extern "C"`` layer of ``include/srcnn_b200.h``).  This module is only the
+thin binding the tests and the benchmark use; it contains no image arithmetic and no fallback: if the library
+is not built, or there is no B200, every entry point raises.
+"""
+import ctypes as C
+import pathlib
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+LIB_PATH = ROOT / "lib" / "libsrcnn.so"
+
+NEAREST, BILINEAR, BICUBIC, LANCZOS3, BSPLINE = range(5)
+CONV_TENSOR, CONV_EXACT = 0, 1
+OK, EINVAL, ESIZE, ENODEV, ECUDA, ENOTHING = 0, -1, -2, -20, -21, -100
+
+_u8p, _f32p, _f64p, _i32p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int))
+_lib = None
+
+
+class SrcnnError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__("libsrcnn-b200 error %d %s" % (code, msg))
+        self.code = code
+
+
+def build():
+    """compile the library in-tree (nvcc, sm_100a)"""
+    import subprocess
+    subprocess.run(["make", "-s", "-C", str(ROOT / "csrc")], check=True)
+
+
+def lib():
+    """the loaded shared library; raises if it has not been built (no fallback of any kind)"""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise SrcnnError(ENODEV, "%s missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        L = C.CDLL(str(LIB_PATH))
+        vp, u, f, i = C.c_void_p, C.c_uint, C.c_float, C.c_int
+        L.srcnn_b200_create.argtypes = [i, C.POINTER(vp)]
+        L.srcnn_b200_destroy.argtypes = [vp]; L.srcnn_b200_destroy.restype = None
+        L.srcnn_b200_last_error.argtypes = [vp]; L.srcnn_b200_last_error.restype = C.c_char_p
+        L.srcnn_b200_set_conv_mode.argtypes = [vp, i]
+        L.srcnn_b200_get_conv_mode.argtypes = [vp]
+        L.srcnn_b200_output_dims.argtypes = [u, u, f, C.POINTER(u), C.POINTER(u)]; L.srcnn_b200_output_dims.restype = None
+        L.srcnn_b200_process_dims.argtypes = [u, u, f, i, C.POINTER(u), C.POINTER(u)]
+        L.srcnn_b200_pass_host.argtypes = [vp, vp, u, u, u, f, i, vp, vp]
+        L.srcnn_b200_pass_host_rows.argtypes = [vp, vp, u, u, u, f, i, u, u, vp, vp]
+        L.srcnn_b200_pass_device.argtypes = [vp, vp, u, u, u, f, i, u, u, vp, vp]
+        L.srcnn_b200_sync.argtypes = [vp]
+        L.srcnn_b200_stream.argtypes = [vp]; L.srcnn_b200_stream.restype = vp
+        L.srcnn_b200_process_host.argtypes = [vp, vp, u, u, u, f, i, i, vp, vp]
+        L.srcnn_b200_batch_host.argtypes = [vp, vp, u, u, u, u, f, i, vp, vp]
+        L.srcnn_b200_host_alloc.argtypes = [C.c_size_t]; L.srcnn_b200_host_alloc.restype = vp
+        L.srcnn_b200_host_free.argtypes = [vp]; L.srcnn_b200_host_free.restype = None
+        L.srcnn_b200_get_plane.argtypes = [vp, i, vp, C.c_size_t, C.POINTER(u), C.POINTER(u), C.POINTER(u)]
+        L.srcnn_b200_set_timing.argtypes = [vp, i]
+        L.srcnn_b200_last_timings.argtypes = [vp, _f32p]
+        L.srcnn_b200_launch_count.argtypes = [vp]; L.srcnn_b200_launch_count.restype = C.c_ulonglong
+        L.srcnn_b200_stage_color_in.argtypes = [vp, vp, u, u, u, C.POINTER(vp)]
+        L.srcnn_b200_stage_resize.argtypes = [vp, vp, u, u, u, u, i, vp]
+        L.srcnn_b200_stage_conv.argtypes = [vp, vp, u, u, i, vp]
+        L.srcnn_b200_stage_color_out.argtypes = [vp, C.POINTER(vp), u, u, u, vp, vp]
+        L.srcnn_b200_contrib_table.argtypes = [i, u, u, _i32p, _i32p, _f64p, i]
+        # the C++ drop-in API, by its (reference-identical) mangled names
+        L.ProcessSRCNN = getattr(L, "_Z12ProcessSRCNNPKhjjjfRPhRjPS1_Pj")
+        L.ProcessSRCNN.restype = i
+        L.ProcessSRCNN.argtypes = [vp, u, u, u, f, C.POINTER(vp), C.POINTER(u), C.POINTER(vp), C.POINTER(u)]
+        L.ConfigureFilterSRCNN = getattr(L, "_Z20ConfigureFilterSRCNN15SRCNNFilterTypeb")
+        L.ConfigureFilterSRCNN.restype = None
+        L.ConfigureFilterSRCNN.argtypes = [i, C.c_bool]
+        _lib = L
+    return _lib
+
+
+def output_dims(w, h, multiply):
+    ow, oh = C.c_uint(), C.c_uint()
+    lib().srcnn_b200_output_dims(w, h, multiply, C.byref(ow), C.byref(oh))
+    return ow.value, oh.value
+
+
+def process_dims(w, h, multiply, stepscale):
+    ow, oh = C.c_uint(), C.c_uint()
+    n = lib().srcnn_b200_process_dims(w, h, multiply, int(bool(stepscale)), C.byref(ow), C.byref(oh))
+    return n, ow.value, oh.value
+
+
+def contrib_table(filt, dst, src, maxwin=64):
+    """host-side contribution table (left, right, weights[dst, maxwin]); needs no GPU"""
+    L = np.zeros(dst, np.int32); R = np.zeros(dst, np.int32); W = np.zeros((dst, maxwin), np.float64)
+    win = lib().srcnn_b200_contrib_table(int(filt), dst, src, L.ctypes.data_as(_i32p), R.ctypes.data_as(_i32p),
+                                         W.ctypes.data_as(_f64p), maxwin)
+    if win < 0:
+        raise SrcnnError(win, "contrib_table")
+    return L, R, W
+
+
+def _vp(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def process_srcnn(img, multiply, filt=BICUBIC, stepscale=False, want_conv=True):
+    """The drop-in C++ API exactly as an application calls it: ConfigureFilterSRCNN + ProcessSRCNN.
+    -> (rc, out | None, conv | None); the new[] buffers are copied and released via libstdc++'s operator delete[]."""
+    L = lib()
+    h, w, d = img.shape
+    img = np.ascontiguousarray(img, np.uint8)
+    L.ConfigureFilterSRCNN(int(filt), bool(stepscale))
+    out, osz, cv, csz = C.c_void_p(), C.c_uint(0), C.c_void_p(), C.c_uint(0)
+    rc = L.ProcessSRCNN(_vp(img), w, h, d, C.c_float(multiply), C.byref(out), C.byref(osz),
+                        C.byref(cv) if want_conv else None, C.byref(csz) if want_conv else None)
+    o = c = None
+    dele = C.CDLL("libstdc++.so.6")._ZdaPv          # operator delete[](void*)
+    dele.argtypes = [C.c_void_p]; dele.restype = None
+    if out.value:
+        o = np.ctypeslib.as_array(C.cast(out, _u8p), (osz.value,)).copy(); dele(out)
+    if cv.value:
+        c = np.ctypeslib.as_array(C.cast(cv, _u8p), (csz.value,)).copy(); dele(cv)
+    return rc, o, c
+
+
+class Context:
+    """one GPU + one stream (include/srcnn_b200.h: srcnn_b200_ctx)"""
+
+    def __init__(self, device=0, conv_mode=CONV_TENSOR):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.srcnn_b200_create(device, C.byref(h))
+        if rc != 0:
+            raise SrcnnError(rc, "srcnn_b200_create(device=%d): no usable B200 (there is no CPU fallback)" % device)
+        self.h = h
+        self.set_conv_mode(conv_mode)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.srcnn_b200_destroy(self.h); self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise SrcnnError(rc, "%s: %s" % (what, (self.L.srcnn_b200_last_error(self.h) or b"").decode()))
+
+    def set_conv_mode(self, mode):
+        self._ck(self.L.srcnn_b200_set_conv_mode(self.h, mode), "set_conv_mode")
+
+    # ---- passes -----------------------------------------------------------------------------------------
+    def pass_host(self, img, multiply, filt=BICUBIC, want_conv=True, rows=None, out=None, conv=None):
+        h, w, d = img.shape
+        img = np.ascontiguousarray(img, np.uint8)
+        ow, oh = output_dims(w, h, multiply)
+        r0, r1 = rows if rows is not None else (0, oh)
+        if out is None:
+            out = np.empty((max(r1 - r0, 0), ow, d), np.uint8)
+        if conv is None and want_conv:
+            conv = np.empty((max(r1 - r0, 0), ow), np.uint8)
+        rc = self.L.srcnn_b200_pass_host_rows(self.h, _vp(img), w, h, d, multiply, int(filt), r0, r1, _vp(out),
+                                              _vp(conv) if want_conv else None)
+        self._ck(rc, "pass_host_rows")
+        return out, (conv if want_conv else None)
+
+    def pass_device(self, d_src, w, h, d, multiply, filt, d_out, d_conv=0, rows=None):
+        """device pointers (ints); asynchronous on the context's stream"""
+        ow, oh = output_dims(w, h, multiply)
+        r0, r1 = rows if rows is not None else (0, oh)
+        self._ck(self.L.srcnn_b200_pass_device(self.h, d_src, w, h, d, multiply, int(filt), r0, r1, d_out,
+                                               d_conv or None), "pass_device")
+
+    def sync(self):
+        self._ck(self.L.srcnn_b200_sync(self.h), "sync")
+
+    @property
+    def stream(self):
+        return self.L.srcnn_b200_stream(self.h)
+
+    def process(self, img, multiply, filt=BICUBIC, stepscale=False, want_conv=True):
+        """whole ProcessSRCNN semantics through the C layer -> (rc, out|None, conv|None)"""
+        h, w, d = img.shape
+        img = np.ascontiguousarray(img, np.uint8)
+        n, ow, oh = process_dims(w, h, multiply, stepscale)
+        if n == 0:
+            return ENOTHING, None, None
+        out = np.empty((oh, ow, d), np.uint8)
+        conv = np.empty((oh, ow), np.uint8) if want_conv else None
+        rc = self.L.srcnn_b200_process_host(self.h, _vp(img), w, h, d, multiply, int(filt), int(bool(stepscale)),
+                                            _vp(out), _vp(conv))
+        if rc != 0:
+            return rc, None, None
+        return rc, out, conv
+
+    def batch(self, frames, multiply, filt=BICUBIC, want_conv=False, out=None):
+        n, h, w, d = frames.shape
+        frames = np.ascontiguousarray(frames, np.uint8)
+        ow, oh = output_dims(w, h, multiply)
+        if out is None:
+            out = np.empty((n, oh, ow, d), np.uint8)
+        conv = np.empty((n, oh, ow), np.uint8) if want_conv else None
+        self._ck(self.L.srcnn_b200_batch_host(self.h, _vp(frames), n, w, h, d, multiply, int(filt), _vp(out), _vp(conv)),
+                 "batch_host")
+        return out, conv
+
+    # ---- introspection ----------------------------------------------------------------------------------
+    def get_plane(self, which, shape_hint):
+        oh, ow = shape_hint
+        buf = np.empty(((oh + 12) * ow,), np.float32)
+        r0, nr, wd = C.c_uint(), C.c_uint(), C.c_uint()
+        self._ck(self.L.srcnn_b200_get_plane(self.h, which, _vp(buf), buf.size, C.byref(r0), C.byref(nr), C.byref(wd)),
+                 "get_plane")
+        return r0.value, buf[: nr.value * wd.value].reshape(nr.value, wd.value).copy()
+
+    def set_timing(self, on=True):
+        self._ck(self.L.srcnn_b200_set_timing(self.h, int(on)), "set_timing")
+
+    def timings(self):
+        ms = (C.c_float * 7)()
+        self._ck(self.L.srcnn_b200_last_timings(self.h, ms), "last_timings")
+        return dict(zip(["color_in", "resize1", "resize2", "pack", "conv", "color_out", "total"], list(ms)))
+
+    @property
+    def launches(self):
+        return int(self.L.srcnn_b200_launch_count(self.h))
+
+    # ---- single stages ----------------------------------------------------------------------------------
+    def color_in(self, img):
+        h, w, d = img.shape
+        img = np.ascontiguousarray(img, np.uint8)
+        pl = [np.empty((h, w), np.float32) for _ in range(d)]
+        arr = (C.c_void_p * d)(*[p.ctypes.data for p in pl])
+        self._ck(self.L.srcnn_b200_stage_color_in(self.h, _vp(img), w, h, d, arr), "stage_color_in")
+        return pl
+
+    def resize(self, plane, dw, dh, filt):
+        sh, sw = plane.shape
+        plane = np.ascontiguousarray(plane, np.float32)
+        o = np.empty((dh, dw), np.float32)
+        self._ck(self.L.srcnn_b200_stage_resize(self.h, _vp(plane), sw, sh, dw, dh, int(filt), _vp(o)), "stage_resize")
+        return o
+
+    def conv(self, y, mode=None):
+        h, w = y.shape
+        y = np.ascontiguousarray(y, np.float32)
+        o = np.empty((h, w), np.float32)
+        if mode is None:
+            mode = self.L.srcnn_b200_get_conv_mode(self.h)
+        self._ck(self.L.srcnn_b200_stage_conv(self.h, _vp(y), w, h, int(mode), _vp(o)), "stage_conv")
+        return o
+
+    def color_out(self, planes, want_conv=False):
+        d = len(planes); h, w = planes[0].shape
+        planes = [np.ascontiguousarray(p, np.float32) for p in planes]
+        arr = (C.c_void_p * d)(*[p.ctypes.data for p in planes])
+        o = np.empty((h, w, d), np.uint8)
+        cv = np.empty((h, w), np.uint8) if want_conv else None
+        self._ck(self.L.srcnn_b200_stage_color_out(self.h, arr, w, h, d, _vp(o), _vp(cv)), "stage_color_out")
+        return (o, cv) if want_conv else o
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array in CUDA pinned host memory (srcnn_b200_host_alloc); keep the returned array alive"""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib().srcnn_b200_host_alloc(n)
+    if not p:
+        raise SrcnnError(ECUDA, "host_alloc(%d)" % n)
+    buf = (C.c_ubyte * n).from_address(p)
+    a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return a

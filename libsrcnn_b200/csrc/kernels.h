@@ -1,0 +1,72 @@
+/* Internal: launchers of the sm_100a kernels (one per stage of the reference's doSRCNN, src/libsrcnn.cpp:628-923).
+ * Host code (srcnn_ctx.cu) talks to the kernels only through these functions. */
+#ifndef SRCNN_B200_KERNELS_H
+#define SRCNN_B200_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace srcnn {
+
+/* per-axis contribution table on the device (built on the host in double, contrib.cpp) */
+struct AxisTableDev {
+    const int*    left;     /* [dst]  first source index           */
+    const int*    count;    /* [dst]  number of taps (right-left+1) */
+    const double* w;        /* [dst][win]                           */
+    int           win;
+};
+
+/* geometry of the FP16 conv-input plane consumed by the tensor-core kernel (see DESIGN.md "Y16 plane") */
+struct Y16Geom {
+    int pitch;      /* halves per row, multiple of 64                                  */
+    int rows;       /* strip rows + 2*6                                                */
+    int bands;      /* ceil(dw / 124) column bands                                     */
+};
+constexpr int kY16PadL   = 8;    /* plane column = image column + 8                    */
+constexpr int kHaloRows  = 6;    /* conv I (4) + conv III (2)                          */
+constexpr int kBandCols  = 124;  /* output columns per 128-lane band                   */
+
+Y16Geom y16_geometry(unsigned dw, unsigned strip_rows);
+
+/* colour-in: u8 interleaved -> d planar FP32 planes of `npix` pixels each (plane p at planes + p*plane_stride) */
+void launch_color_in(const uint8_t* src, size_t npix, unsigned d, float* planes, size_t plane_stride,
+                     cudaStream_t s);
+
+/* one separable pass along rows (vertical) or columns (horizontal) for nplanes planes at once.
+ * Plane 0 uses table ty, planes >= 1 use table tc (reference src/libsrcnn.cpp:675-714).
+ *  vertical  : in  [in_rows ][width] with in-row 0 = global source row in_row0
+ *              out [out_rows][width] with out-row 0 = global destination row out_row0
+ *  horizontal: in  [rows][sw] -> out [rows][dw]                                                         */
+void launch_resize_vertical(const float* in, size_t in_plane_stride, unsigned width, unsigned in_row0,
+                            float* out, size_t out_plane_stride, unsigned out_row0, unsigned out_rows,
+                            unsigned nplanes, AxisTableDev ty, AxisTableDev tc, cudaStream_t s);
+void launch_resize_horizontal(const float* in, size_t in_plane_stride, unsigned sw,
+                              float* out, size_t out_plane_stride, unsigned dw, unsigned rows,
+                              unsigned nplanes, AxisTableDev ty, AxisTableDev tc, cudaStream_t s);
+
+/* conv-input pack: FP32 Y window (rows [win_row0, win_row0+win_rows) of a dw x dh plane) -> replicate-padded FP16
+ * plane covering global rows strip_row0-6 .. strip_row1+6 (clamped) and columns -8 .. pitch-9 (clamped) */
+void launch_pack_y16(const float* y, unsigned dw, unsigned dh, unsigned win_row0,
+                     __half* y16, Y16Geom g, unsigned strip_row0, cudaStream_t s);
+
+/* fused conv I+II+III, bit-exact FP32 CUDA-core path (validation mode).
+ * y: window rows [win_row0, ...) of the dw x dh interpolated plane; out: rows [row0,row1) x dw */
+void launch_conv_exact(const float* y, unsigned dw, unsigned dh, unsigned win_row0, unsigned win_rows,
+                       float* out, unsigned row0, unsigned row1, cudaStream_t s);
+int  conv_exact_init();    /* uploads the FP32 parameter tables to __constant__ memory of the current device */
+
+/* fused conv I+II+III, tcgen05 / TMEM / TMA path (product mode) -- conv_tc.cu */
+struct ConvTcState;                         /* per-context: device weights image, tensor maps */
+int  conv_tc_create(ConvTcState** st);      /* 0 ok */
+void conv_tc_destroy(ConvTcState* st);
+int  launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, unsigned dh,
+                    float* out, unsigned row0, unsigned row1, int num_sms, cudaStream_t s);
+const char* conv_tc_error(const ConvTcState* st);
+
+/* colour-out: Y' + Cb/Cr/(A) -> interleaved u8 (+ optional u8 conv plane); all arrays are `npix` long views */
+void launch_color_out(const float* yprime, const float* cb, const float* cr, const float* a, size_t npix,
+                      unsigned d, uint8_t* out, uint8_t* conv, cudaStream_t s);
+
+} // namespace srcnn
+#endif

@@ -1,0 +1,682 @@
+/* Context, pass orchestration and the extern "C" layer (include/srcnn_b200.h).
+ *
+ * One pass = reference libsrcnn::doSRCNN (src/libsrcnn.cpp:628-923) as a launch sequence on one stream:
+ *   colour-in -> resize pass 1 -> resize pass 2 -> conv-input pack -> fused conv I/II/III -> colour-out
+ * restricted to the output rows [row0,row1) of a strip (the whole image for the ordinary call) plus the 6-row
+ * halo of interpolated Y the convolutions need.  No CPU arithmetic on image data anywhere in this file.
+ */
+#include "../../include/srcnn_b200.h"
+#include "kernels.h"
+#include "contrib.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <algorithm>
+
+using namespace srcnn;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = bytes + bytes / 8 + 256;          /* grow-only with slack */
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct TableDev {
+    AxisTable host;
+    void* dev = nullptr;
+    AxisTableDev view{};
+};
+
+/* geometry of one pass restricted to a row strip */
+struct Plan {
+    unsigned w, h, d, ow, oh;
+    unsigned r0, r1;        /* output rows produced                                   */
+    unsigned e0, e1;        /* rows of the resized planes computed (strip + conv halo) */
+    unsigned s0, s1;        /* source rows read                                        */
+    int fy, fc;             /* filter of plane 0 / of the other planes                 */
+    bool hfirst;            /* ow <= w: horizontal pass first (src/frawscale.cpp:195)  */
+    bool need_h, need_v;
+};
+
+} // namespace
+
+struct srcnn_b200_ctx {
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
+    DevBuf src8[2], planes_src, tmp, planes_dst, y16, yprime, out8[2], conv8[2], chain[2];
+    PinBuf pin_in[2], pin_out[2], pin_conv[2];
+    std::map<std::tuple<int, unsigned, unsigned>, TableDev*> tables;
+    ConvTcState* tc = nullptr;
+    int conv_mode = SRCNN_B200_CONV_TENSOR;
+    bool timing = false;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
+    float ms[7] = {};
+    unsigned long long launches = 0;
+    std::string err;
+    /* last pass, for the plane getters */
+    Plan last{}; bool have_last = false; size_t last_plane_stride = 0;
+};
+
+namespace {
+
+int fail_cuda(srcnn_b200_ctx* c, cudaError_t e, const char* what)
+{
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    c->err = buf;
+    return SRCNN_B200_ECUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call); } while (0)
+
+int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, TableDev** out)
+{
+    auto key = std::make_tuple(filter, dst, src);
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end()) { *out = it->second; return 0; }
+    TableDev* t = new TableDev;
+    build_axis_table(filter, dst, src, t->host);
+    const size_t ints = (size_t)dst * sizeof(int);
+    const size_t ints_al = (2 * ints + 15) / 16 * 16;
+    const size_t bytes = ints_al + t->host.w.size() * sizeof(double);
+    std::vector<unsigned char> img(bytes, 0);
+    int* L = reinterpret_cast<int*>(img.data());
+    int* C = L + dst;
+    for (unsigned u = 0; u < dst; u++) { L[u] = t->host.left[u]; C[u] = t->host.right[u] - t->host.left[u] + 1; }
+    memcpy(img.data() + ints_al, t->host.w.data(), t->host.w.size() * sizeof(double));
+    cudaError_t e = cudaMalloc(&t->dev, bytes);
+    if (e != cudaSuccess) { delete t; return fail_cuda(ctx, e, "cudaMalloc(table)"); }
+    e = cudaMemcpyAsync(t->dev, img.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);      /* img is a temporary */
+    if (e != cudaSuccess) { cudaFree(t->dev); delete t; return fail_cuda(ctx, e, "upload(table)"); }
+    t->view.left  = reinterpret_cast<const int*>(t->dev);
+    t->view.count = t->view.left + dst;
+    t->view.w     = reinterpret_cast<const double*>(static_cast<unsigned char*>(t->dev) + ints_al);
+    t->view.win   = t->host.win;
+    ctx->tables[key] = t;
+    *out = t;
+    return 0;
+}
+
+int make_plan(unsigned w, unsigned h, unsigned d, float multiply, int filter, unsigned row0, unsigned row1, Plan& p)
+{
+    if (!w || !h || (d != 3 && d != 4)) return SRCNN_B200_EINVAL;
+    if ((float)w * multiply <= 0.f || (float)h * multiply <= 0.f) return SRCNN_B200_ESIZE;
+    p.w = w; p.h = h; p.d = d;
+    srcnn_b200_output_dims(w, h, multiply, &p.ow, &p.oh);
+    if (!p.ow || !p.oh) return SRCNN_B200_ESIZE;
+    if (row1 > p.oh || row0 >= row1) return SRCNN_B200_EINVAL;
+    if (p.oh > 65535u || h > 65535u) return SRCNN_B200_EINVAL;      /* rows map to gridDim.y */
+    p.r0 = row0; p.r1 = row1;
+    p.e0 = row0 > (unsigned)kHaloRows ? row0 - kHaloRows : 0;
+    p.e1 = std::min(p.oh, row1 + kHaloRows);
+    p.fy = (filter >= kNearest && filter <= kBspline) ? filter : kNearest;   /* src/libsrcnn.cpp:677-699 */
+    p.fc = (filter == kNearest) ? kNearest : kBilinear;                      /* src/libsrcnn.cpp:703-713 */
+    p.hfirst = (p.ow <= w);
+    p.need_h = (p.ow != w); p.need_v = (p.oh != h);
+    return 0;
+}
+
+struct Stamp {
+    srcnn_b200_ctx* c; int i = 0;
+    explicit Stamp(srcnn_b200_ctx* c_) : c(c_) { mark(); }
+    void mark() { if (c->timing && i < 8) cudaEventRecord(c->ev[i], c->stream); i++; }
+};
+
+/* d_src points at source row p.s0 (device); d_out/d_conv at output row p.r0 (device).  Asynchronous. */
+int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, bool src_is_whole_image,
+             uint8_t* d_out, uint8_t* d_conv)
+{
+    TableDev *vy = nullptr, *vc = nullptr, *hy = nullptr, *hc = nullptr;
+    int rc;
+    if (p.need_v) {
+        if ((rc = get_table(ctx, p.fy, p.oh, p.h, &vy))) return rc;
+        if ((rc = get_table(ctx, p.fc, p.oh, p.h, &vc))) return rc;
+        int lo = INT32_MAX, hi = -1;
+        for (unsigned r = p.e0; r < p.e1; r++) {
+            lo = std::min(lo, std::min(vy->host.left[r], vc->host.left[r]));
+            hi = std::max(hi, std::max(vy->host.right[r], vc->host.right[r]));
+        }
+        p.s0 = (unsigned)lo; p.s1 = (unsigned)hi + 1;
+    } else { p.s0 = p.e0; p.s1 = p.e1; }
+    if (p.need_h) {
+        if ((rc = get_table(ctx, p.fy, p.ow, p.w, &hy))) return rc;
+        if ((rc = get_table(ctx, p.fc, p.ow, p.w, &hc))) return rc;
+    }
+    const uint8_t* d_src = src_is_whole_image ? d_src_base + (size_t)p.s0 * p.w * p.d : d_src_base;
+
+    const unsigned srows = p.s1 - p.s0, erows = p.e1 - p.e0, orows = p.r1 - p.r0;
+    auto al = [](size_t n) { return (n + 63) / 64 * 64; };
+    const size_t ps_src = al((size_t)srows * p.w), ps_dst = al((size_t)erows * p.ow);
+    const size_t ps_tmp = al(p.hfirst ? (size_t)srows * p.ow : (size_t)erows * p.w);
+    CK(ctx->planes_src.ensure(ps_src * p.d * sizeof(float)));
+    CK(ctx->planes_dst.ensure(ps_dst * p.d * sizeof(float)));
+    if (p.need_h && p.need_v) CK(ctx->tmp.ensure(ps_tmp * p.d * sizeof(float)));
+    CK(ctx->yprime.ensure((size_t)orows * p.ow * sizeof(float)));
+    float* P_src = static_cast<float*>(ctx->planes_src.p);
+    float* P_dst = static_cast<float*>(ctx->planes_dst.p);
+    float* P_tmp = static_cast<float*>(ctx->tmp.p);
+    float* Yp    = static_cast<float*>(ctx->yprime.p);
+    cudaStream_t s = ctx->stream;
+
+    Stamp st(ctx);
+    /* 1. colour-in on the source rows the strip needs */
+    launch_color_in(d_src, (size_t)srows * p.w, p.d, P_src, ps_src, s); ctx->launches++;
+    st.mark();
+    /* 2./3. separable resize; order as in FRAWResizeEngine::scale (src/frawscale.cpp:195-278) */
+    const AxisTableDev none{};
+    if (!p.need_h && !p.need_v) {
+        /* equal size: plain copy of every plane (the reference copies only half of it, a bug we do not keep) */
+        for (unsigned pl = 0; pl < p.d; pl++)
+            CK(cudaMemcpyAsync(P_dst + pl * ps_dst, P_src + pl * ps_src, (size_t)erows * p.ow * sizeof(float),
+                               cudaMemcpyDeviceToDevice, s));
+        st.mark(); st.mark();
+    } else if (p.hfirst) {
+        if (p.need_h) {
+            float* o = p.need_v ? P_tmp : P_dst; const size_t os = p.need_v ? ps_tmp : ps_dst;
+            launch_resize_horizontal(P_src, ps_src, p.w, o, os, p.ow, srows, p.d, hy->view, hc->view, s); ctx->launches++;
+        }
+        st.mark();
+        if (p.need_v) {
+            const float* i = p.need_h ? P_tmp : P_src; const size_t is = p.need_h ? ps_tmp : ps_src;
+            launch_resize_vertical(i, is, p.ow, p.s0, P_dst, ps_dst, p.e0, erows, p.d, vy->view, vc->view, s); ctx->launches++;
+        }
+        st.mark();
+    } else {
+        if (p.need_v) {
+            float* o = p.need_h ? P_tmp : P_dst; const size_t os = p.need_h ? ps_tmp : ps_dst;
+            launch_resize_vertical(P_src, ps_src, p.w, p.s0, o, os, p.e0, erows, p.d, vy->view, vc->view, s); ctx->launches++;
+        }
+        st.mark();
+        if (p.need_h) {
+            const float* i = p.need_v ? P_tmp : P_src; const size_t is = p.need_v ? ps_tmp : ps_src;
+            launch_resize_horizontal(i, is, p.w, P_dst, ps_dst, p.ow, erows, p.d, hy->view, hc->view, s); ctx->launches++;
+        }
+        st.mark();
+    }
+    (void)none;
+    /* 4./5. fused conv I+II+III on the Y plane */
+    if (ctx->conv_mode == SRCNN_B200_CONV_TENSOR) {
+        const Y16Geom g = y16_geometry(p.ow, orows);
+        CK(ctx->y16.ensure((size_t)g.pitch * g.rows * sizeof(__half)));
+        launch_pack_y16(P_dst, p.ow, p.oh, p.e0, static_cast<__half*>(ctx->y16.p), g, p.r0, s); ctx->launches++;
+        st.mark();
+        if (launch_conv_tc(ctx->tc, static_cast<const __half*>(ctx->y16.p), g, p.ow, p.oh, Yp, p.r0, p.r1,
+                           ctx->num_sms, s)) {
+            ctx->err = std::string("conv_tc: ") + conv_tc_error(ctx->tc);
+            return SRCNN_B200_ECUDA;
+        }
+        ctx->launches++;
+    } else {
+        st.mark();
+        launch_conv_exact(P_dst, p.ow, p.oh, p.e0, erows, Yp, p.r0, p.r1, s); ctx->launches++;
+    }
+    st.mark();
+    /* 6. colour-out (+ conv plane) for the strip rows */
+    const size_t off = (size_t)(p.r0 - p.e0) * p.ow;
+    launch_color_out(Yp, P_dst + ps_dst + off, P_dst + 2 * ps_dst + off, p.d == 4 ? P_dst + 3 * ps_dst + off : nullptr,
+                     (size_t)orows * p.ow, p.d, d_out, d_conv, s); ctx->launches++;
+    st.mark();
+    CK(cudaGetLastError());
+    ctx->last = p; ctx->have_last = true; ctx->last_plane_stride = ps_dst;
+    return 0;
+}
+
+int collect_timing(srcnn_b200_ctx* ctx)
+{
+    if (!ctx->timing) return 0;
+    for (int i = 0; i < 6; i++) {
+        float v = 0.f;
+        if (cudaEventElapsedTime(&v, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) v = -1.f;
+        ctx->ms[i] = v;
+    }
+    float v = 0.f;
+    if (cudaEventElapsedTime(&v, ctx->ev[0], ctx->ev[6]) != cudaSuccess) v = -1.f;
+    ctx->ms[6] = v;
+    return 0;
+}
+
+} // namespace
+
+/* ================================================================ extern "C" ================================ */
+
+extern "C" {
+
+int srcnn_b200_abi_version(void) { return SRCNN_B200_ABI_VERSION; }
+
+int srcnn_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int srcnn_b200_create(int device, srcnn_b200_ctx** out)
+{
+    if (!out) return SRCNN_B200_EINVAL;
+    *out = nullptr;
+    int n = srcnn_b200_device_count();
+    if (n <= 0 || device < 0 || device >= n) return SRCNN_B200_ENODEV;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return SRCNN_B200_ENODEV; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return SRCNN_B200_ENODEV; }
+    if (prop.major != 10) {     /* the kernels are sm_100a only: no other architecture, no CPU fallback */
+        fprintf(stderr, "libsrcnn-b200: device %d is sm_%d%d, this build needs sm_100 (B200)\n", device, prop.major, prop.minor);
+        return SRCNN_B200_ENODEV;
+    }
+    srcnn_b200_ctx* ctx = new srcnn_b200_ctx;
+    ctx->device = device; ctx->num_sms = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    for (int i = 0; ok && i < 2; i++)
+        ok = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = conv_exact_init() == 0;
+    if (ok) ok = conv_tc_create(&ctx->tc) == 0;
+    if (!ok) {
+        fprintf(stderr, "libsrcnn-b200: context creation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        srcnn_b200_destroy(ctx);
+        return SRCNN_B200_ENODEV;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void srcnn_b200_destroy(srcnn_b200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->tables) { cudaFree(kv.second->dev); delete kv.second; }
+    if (ctx->tc) conv_tc_destroy(ctx->tc);
+    for (int i = 0; i < 2; i++) {
+        ctx->src8[i].release(); ctx->out8[i].release(); ctx->conv8[i].release(); ctx->chain[i].release();
+        ctx->pin_in[i].release(); ctx->pin_out[i].release(); ctx->pin_conv[i].release();
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
+    ctx->planes_src.release(); ctx->tmp.release(); ctx->planes_dst.release(); ctx->y16.release(); ctx->yprime.release();
+    for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
+    if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
+    delete ctx;
+}
+
+const char* srcnn_b200_last_error(const srcnn_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int srcnn_b200_set_conv_mode(srcnn_b200_ctx* ctx, int mode)
+{
+    if (!ctx || (mode != SRCNN_B200_CONV_TENSOR && mode != SRCNN_B200_CONV_EXACT)) return SRCNN_B200_EINVAL;
+    ctx->conv_mode = mode; return 0;
+}
+int srcnn_b200_get_conv_mode(const srcnn_b200_ctx* ctx) { return ctx ? ctx->conv_mode : SRCNN_B200_EINVAL; }
+
+void srcnn_b200_output_dims(unsigned w, unsigned h, float multiply, unsigned* ow, unsigned* oh)
+{
+    /* unsigned = unsigned * float: evaluated in float, truncated (src/libsrcnn.cpp:662-663) */
+    const float fw = (float)w * multiply, fh = (float)h * multiply;
+    if (ow) *ow = fw > 0.f ? (unsigned)fw : 0u;
+    if (oh) *oh = fh > 0.f ? (unsigned)fh : 0u;
+}
+
+/* step-scale schedule (src/libsrcnn.cpp:980-1061): factors[] of the passes that actually run */
+static int step_schedule(unsigned w, float multiply, float* factors, int maxn)
+{
+    const float lf = fmodf(multiply, 2.f);
+    int repeat = (int)(multiply / 2.f);
+    if (lf > 0.f) repeat++;
+    unsigned sw = w; int n = 0;
+    for (int cnt = 0; cnt < repeat && n < maxn; cnt++) {
+        float m = 2.0f;
+        if (cnt + 1 == repeat) {
+            m = ((float)w * multiply) / (float)sw;
+            if (m == 0.f || m == 1.0f) break;
+        }
+        factors[n++] = m;
+        if (repeat > 1) sw = (unsigned)((float)sw * m);
+    }
+    return n;
+}
+
+int srcnn_b200_process_dims(unsigned w, unsigned h, float multiply, int stepscale, unsigned* ow, unsigned* oh)
+{
+    unsigned cw = w, ch = h;
+    if (!stepscale) { srcnn_b200_output_dims(w, h, multiply, &cw, &ch); if (ow) *ow = cw; if (oh) *oh = ch; return 1; }
+    float f[64];
+    const int n = step_schedule(w, multiply, f, 64);
+    for (int i = 0; i < n; i++) {
+        /* output of a pass from doSRCNN's own size rule; the loop's running sw/sh (:1047-1051) use the same
+         * float product when more than one pass runs */
+        unsigned nw, nh; srcnn_b200_output_dims(cw, ch, f[i], &nw, &nh); cw = nw; ch = nh;
+    }
+    if (ow) *ow = n ? cw : 0; if (oh) *oh = n ? ch : 0;
+    return n;
+}
+
+int srcnn_b200_pass_device(srcnn_b200_ctx* ctx, const void* d_src, unsigned w, unsigned h, unsigned d,
+                           float multiply, int filter, unsigned row0, unsigned row1, void* d_out, void* d_conv)
+{
+    if (!ctx || !d_src || !d_out) return SRCNN_B200_EINVAL;
+    Plan p; int rc = make_plan(w, h, d, multiply, filter, row0, row1, p);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return run_pass(ctx, p, static_cast<const uint8_t*>(d_src), true, static_cast<uint8_t*>(d_out),
+                    static_cast<uint8_t*>(d_conv));
+}
+
+int srcnn_b200_sync(srcnn_b200_ctx* ctx)
+{
+    if (!ctx) return SRCNN_B200_EINVAL;
+    CK(cudaStreamSynchronize(ctx->stream));
+    collect_timing(ctx);
+    return 0;
+}
+void* srcnn_b200_stream(srcnn_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int srcnn_b200_pass_host_rows(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                              float multiply, int filter, unsigned row0, unsigned row1,
+                              uint8_t* out_rows, uint8_t* conv_rows)
+{
+    if (!ctx || !src || !out_rows) return SRCNN_B200_EINVAL;
+    Plan p; int rc = make_plan(w, h, d, multiply, filter, row0, row1, p);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    /* source rows needed: resolve the vertical tables first (run_pass repeats the lookup from the cache) */
+    {
+        TableDev *vy, *vc;
+        if (p.need_v) {
+            if ((rc = get_table(ctx, p.fy, p.oh, p.h, &vy))) return rc;
+            if ((rc = get_table(ctx, p.fc, p.oh, p.h, &vc))) return rc;
+            int lo = INT32_MAX, hi = -1;
+            for (unsigned r = p.e0; r < p.e1; r++) {
+                lo = std::min(lo, std::min(vy->host.left[r], vc->host.left[r]));
+                hi = std::max(hi, std::max(vy->host.right[r], vc->host.right[r]));
+            }
+            p.s0 = (unsigned)lo; p.s1 = (unsigned)hi + 1;
+        } else { p.s0 = p.e0; p.s1 = p.e1; }
+    }
+    const size_t in_bytes = (size_t)(p.s1 - p.s0) * w * d;
+    const size_t out_bytes = (size_t)(row1 - row0) * p.ow * d, conv_bytes = (size_t)(row1 - row0) * p.ow;
+    CK(ctx->src8[0].ensure(in_bytes));
+    CK(ctx->out8[0].ensure(out_bytes));
+    if (conv_rows) CK(ctx->conv8[0].ensure(conv_bytes));
+    CK(cudaMemcpyAsync(ctx->src8[0].p, src + (size_t)p.s0 * w * d, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = run_pass(ctx, p, static_cast<const uint8_t*>(ctx->src8[0].p), false, static_cast<uint8_t*>(ctx->out8[0].p),
+                  conv_rows ? static_cast<uint8_t*>(ctx->conv8[0].p) : nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_rows, ctx->out8[0].p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (conv_rows) CK(cudaMemcpyAsync(conv_rows, ctx->conv8[0].p, conv_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    collect_timing(ctx);
+    return 0;
+}
+
+int srcnn_b200_pass_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                         float multiply, int filter, uint8_t* out, uint8_t* conv)
+{
+    unsigned ow = 0, oh = 0;
+    if (!w || !h || (d != 3 && d != 4)) return SRCNN_B200_EINVAL;
+    if ((float)w * multiply <= 0.f || (float)h * multiply <= 0.f) return SRCNN_B200_ESIZE;
+    srcnn_b200_output_dims(w, h, multiply, &ow, &oh);
+    if (!ow || !oh) return SRCNN_B200_ESIZE;
+    return srcnn_b200_pass_host_rows(ctx, src, w, h, d, multiply, filter, 0, oh, out, conv);
+}
+
+int srcnn_b200_process_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                            float multiply, int filter, int stepscale, uint8_t* out, uint8_t* conv)
+{
+    if (!ctx || !src || !w || !h || !d) return SRCNN_B200_EINVAL;
+    if (d != 3 && d != 4) return SRCNN_B200_EINVAL;
+    if ((float)w * multiply <= 0.f || (float)h * multiply <= 0.f) return SRCNN_B200_ESIZE;
+    if (!stepscale) return srcnn_b200_pass_host(ctx, src, w, h, d, multiply, filter, out, conv);
+
+    float f[64];
+    const int n = step_schedule(w, multiply, f, 64);
+    if (n == 0) return SRCNN_B200_ENOTHING;
+    if (n == 1) return srcnn_b200_pass_host(ctx, src, w, h, d, f[0], filter, out, conv);
+    if (!out) return SRCNN_B200_EINVAL;
+    /* chain: 8-bit RGB(A) intermediates stay in HBM (the reference round-trips them through host buffers,
+     * src/libsrcnn.cpp:999-1051; the quantisation to 8 bit between passes is preserved) */
+    CK(cudaSetDevice(ctx->device));
+    unsigned cw = w, ch = h;
+    CK(ctx->chain[0].ensure((size_t)w * h * d));
+    CK(cudaMemcpyAsync(ctx->chain[0].p, src, (size_t)w * h * d, cudaMemcpyHostToDevice, ctx->stream));
+    int cur = 0;
+    for (int i = 0; i < n; i++) {
+        Plan p; int rc = make_plan(cw, ch, d, f[i], filter, 0, 1, p);
+        if (rc) return rc;
+        rc = make_plan(cw, ch, d, f[i], filter, 0, p.oh, p);
+        if (rc) return rc;
+        const bool last = (i + 1 == n);
+        const size_t ob = (size_t)p.ow * p.oh * d;
+        CK(ctx->chain[cur ^ 1].ensure(ob));
+        if (last && conv) CK(ctx->conv8[0].ensure((size_t)p.ow * p.oh));
+        rc = run_pass(ctx, p, static_cast<const uint8_t*>(ctx->chain[cur].p), true,
+                      static_cast<uint8_t*>(ctx->chain[cur ^ 1].p),
+                      (last && conv) ? static_cast<uint8_t*>(ctx->conv8[0].p) : nullptr);
+        if (rc) return rc;
+        cur ^= 1; cw = p.ow; ch = p.oh;
+    }
+    CK(cudaMemcpyAsync(out, ctx->chain[cur].p, (size_t)cw * ch * d, cudaMemcpyDeviceToHost, ctx->stream));
+    if (conv) CK(cudaMemcpyAsync(conv, ctx->conv8[0].p, (size_t)cw * ch, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    collect_timing(ctx);
+    return 0;
+}
+
+int srcnn_b200_batch_host(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n, unsigned w, unsigned h,
+                          unsigned d, float multiply, int filter, uint8_t* out, uint8_t* conv)
+{
+    if (!ctx || !frames || !out) return SRCNN_B200_EINVAL;
+    if (n == 0) return 0;
+    Plan p0; int rc = make_plan(w, h, d, multiply, filter, 0, 1, p0);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t ib = (size_t)w * h * d, ob = (size_t)p0.ow * p0.oh * d, cb = (size_t)p0.ow * p0.oh;
+    for (int i = 0; i < 2; i++) {
+        CK(ctx->src8[i].ensure(ib)); CK(ctx->out8[i].ensure(ob));
+        if (conv) CK(ctx->conv8[i].ensure(cb));
+    }
+    /* three-stage software pipeline over frames: upload (stream_in) | kernels (stream) | download (stream_out),
+     * double-buffered device input/output so frame i+1 uploads and frame i-1 downloads while frame i computes */
+    for (unsigned i = 0; i < n; i++) {
+        const int b = (int)(i & 1);
+        if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream_in, ctx->ev_k[b], 0));      /* src8[b] consumed by frame i-2 */
+        CK(cudaMemcpyAsync(ctx->src8[b].p, frames + (size_t)i * ib, ib, cudaMemcpyHostToDevice, ctx->stream_in));
+        CK(cudaEventRecord(ctx->ev_in[b], ctx->stream_in));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));       /* out8[b] drained by frame i-2 */
+        Plan p; make_plan(w, h, d, multiply, filter, 0, p0.oh, p);
+        rc = run_pass(ctx, p, static_cast<const uint8_t*>(ctx->src8[b].p), true, static_cast<uint8_t*>(ctx->out8[b].p),
+                      conv ? static_cast<uint8_t*>(ctx->conv8[b].p) : nullptr);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream_out, ctx->ev_k[b], 0));
+        CK(cudaMemcpyAsync(out + (size_t)i * ob, ctx->out8[b].p, ob, cudaMemcpyDeviceToHost, ctx->stream_out));
+        if (conv) CK(cudaMemcpyAsync(conv + (size_t)i * cb, ctx->conv8[b].p, cb, cudaMemcpyDeviceToHost, ctx->stream_out));
+        CK(cudaEventRecord(ctx->ev_out[b], ctx->stream_out));
+    }
+    CK(cudaStreamSynchronize(ctx->stream_out));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void* srcnn_b200_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void srcnn_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int srcnn_b200_get_plane(srcnn_b200_ctx* ctx, int which, float* host, size_t cap,
+                         unsigned* row0, unsigned* rows, unsigned* width)
+{
+    if (!ctx || !ctx->have_last || !host || which < 0 || which > 4) return SRCNN_B200_EINVAL;
+    const Plan& p = ctx->last;
+    if (which == 3 && p.d != 4) return SRCNN_B200_EINVAL;
+    const float* srcp; unsigned r0, nr;
+    if (which == 4) { srcp = static_cast<const float*>(ctx->yprime.p); r0 = p.r0; nr = p.r1 - p.r0; }
+    else { srcp = static_cast<const float*>(ctx->planes_dst.p) + (size_t)which * ctx->last_plane_stride; r0 = p.e0; nr = p.e1 - p.e0; }
+    const size_t n = (size_t)nr * p.ow;
+    if (cap < n) return SRCNN_B200_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host, srcp, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (row0) *row0 = r0; if (rows) *rows = nr; if (width) *width = p.ow;
+    return 0;
+}
+
+int srcnn_b200_set_timing(srcnn_b200_ctx* ctx, int on) { if (!ctx) return SRCNN_B200_EINVAL; ctx->timing = on != 0; return 0; }
+int srcnn_b200_last_timings(srcnn_b200_ctx* ctx, float* ms7)
+{
+    if (!ctx || !ms7) return SRCNN_B200_EINVAL;
+    memcpy(ms7, ctx->ms, sizeof(ctx->ms)); return 0;
+}
+unsigned long long srcnn_b200_launch_count(const srcnn_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* ---------------------------------------------------------------- single stages (parity tests) */
+
+int srcnn_b200_stage_color_in(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                              float* const* planes)
+{
+    if (!ctx || !src || !planes || !w || !h || (d != 3 && d != 4)) return SRCNN_B200_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)w * h, ps = (n + 63) / 64 * 64;
+    CK(ctx->src8[0].ensure(n * d)); CK(ctx->planes_src.ensure(ps * d * sizeof(float)));
+    CK(cudaMemcpyAsync(ctx->src8[0].p, src, n * d, cudaMemcpyHostToDevice, ctx->stream));
+    launch_color_in(static_cast<const uint8_t*>(ctx->src8[0].p), n, d, static_cast<float*>(ctx->planes_src.p), ps, ctx->stream);
+    ctx->launches++;
+    for (unsigned i = 0; i < d; i++)
+        CK(cudaMemcpyAsync(planes[i], static_cast<float*>(ctx->planes_src.p) + i * ps, n * sizeof(float),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int srcnn_b200_stage_resize(srcnn_b200_ctx* ctx, const float* src, unsigned sw, unsigned sh,
+                            unsigned dw, unsigned dh, int filter, float* dst)
+{
+    if (!ctx || !src || !dst || !sw || !sh || !dw || !dh) return SRCNN_B200_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const int f = (filter >= kNearest && filter <= kBspline) ? filter : kNearest;
+    const size_t ns = (size_t)sw * sh, nd = (size_t)dw * dh;
+    const bool hfirst = dw <= sw, need_h = dw != sw, need_v = dh != sh;
+    const size_t nt = hfirst ? (size_t)dw * sh : (size_t)sw * dh;
+    CK(ctx->planes_src.ensure(ns * sizeof(float))); CK(ctx->planes_dst.ensure(nd * sizeof(float)));
+    CK(ctx->tmp.ensure(nt * sizeof(float)));
+    float *A = static_cast<float*>(ctx->planes_src.p), *T = static_cast<float*>(ctx->tmp.p), *B = static_cast<float*>(ctx->planes_dst.p);
+    CK(cudaMemcpyAsync(A, src, ns * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    TableDev *tv = nullptr, *th = nullptr; int rc;
+    if (need_v && (rc = get_table(ctx, f, dh, sh, &tv))) return rc;
+    if (need_h && (rc = get_table(ctx, f, dw, sw, &th))) return rc;
+    cudaStream_t s = ctx->stream;
+    if (!need_h && !need_v) {
+        CK(cudaMemcpyAsync(B, A, ns * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else if (hfirst) {
+        if (need_h) { launch_resize_horizontal(A, 0, sw, need_v ? T : B, 0, dw, sh, 1, th->view, th->view, s); ctx->launches++; }
+        if (need_v) { launch_resize_vertical(need_h ? T : A, 0, dw, 0, B, 0, 0, dh, 1, tv->view, tv->view, s); ctx->launches++; }
+    } else {
+        if (need_v) { launch_resize_vertical(A, 0, sw, 0, need_h ? T : B, 0, 0, dh, 1, tv->view, tv->view, s); ctx->launches++; }
+        if (need_h) { launch_resize_horizontal(need_v ? T : A, 0, sw, B, 0, dw, dh, 1, th->view, th->view, s); ctx->launches++; }
+    }
+    CK(cudaMemcpyAsync(dst, B, nd * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int srcnn_b200_stage_conv(srcnn_b200_ctx* ctx, const float* y, unsigned w, unsigned h, int mode, float* out)
+{
+    if (!ctx || !y || !out || !w || !h) return SRCNN_B200_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)w * h;
+    CK(ctx->planes_dst.ensure(n * sizeof(float))); CK(ctx->yprime.ensure(n * sizeof(float)));
+    float* Y = static_cast<float*>(ctx->planes_dst.p); float* O = static_cast<float*>(ctx->yprime.p);
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(Y, y, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (mode == SRCNN_B200_CONV_EXACT) {
+        launch_conv_exact(Y, w, h, 0, h, O, 0, h, s); ctx->launches++;
+    } else if (mode == SRCNN_B200_CONV_TENSOR) {
+        const Y16Geom g = y16_geometry(w, h);
+        CK(ctx->y16.ensure((size_t)g.pitch * g.rows * sizeof(__half)));
+        launch_pack_y16(Y, w, h, 0, static_cast<__half*>(ctx->y16.p), g, 0, s); ctx->launches++;
+        if (launch_conv_tc(ctx->tc, static_cast<const __half*>(ctx->y16.p), g, w, h, O, 0, h, ctx->num_sms, s)) {
+            ctx->err = std::string("conv_tc: ") + conv_tc_error(ctx->tc);
+            return SRCNN_B200_ECUDA;
+        }
+        ctx->launches++;
+    } else return SRCNN_B200_EINVAL;
+    CK(cudaMemcpyAsync(out, O, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int srcnn_b200_stage_color_out(srcnn_b200_ctx* ctx, const float* const* planes, unsigned w, unsigned h,
+                               unsigned d, uint8_t* out, uint8_t* conv)
+{
+    if (!ctx || !planes || !out || !w || !h || (d != 3 && d != 4)) return SRCNN_B200_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)w * h, ps = (n + 63) / 64 * 64;
+    CK(ctx->planes_dst.ensure(ps * d * sizeof(float))); CK(ctx->out8[0].ensure(n * d)); CK(ctx->conv8[0].ensure(n));
+    float* P = static_cast<float*>(ctx->planes_dst.p);
+    cudaStream_t s = ctx->stream;
+    for (unsigned i = 0; i < d; i++) CK(cudaMemcpyAsync(P + i * ps, planes[i], n * sizeof(float), cudaMemcpyHostToDevice, s));
+    launch_color_out(P, P + ps, P + 2 * ps, d == 4 ? P + 3 * ps : nullptr, n, d, static_cast<uint8_t*>(ctx->out8[0].p),
+                     conv ? static_cast<uint8_t*>(ctx->conv8[0].p) : nullptr, s);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, ctx->out8[0].p, n * d, cudaMemcpyDeviceToHost, s));
+    if (conv) CK(cudaMemcpyAsync(conv, ctx->conv8[0].p, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int srcnn_b200_contrib_table(int filter, unsigned dst, unsigned src, int* left, int* right, double* weights, int maxwin)
+{
+    if (!dst || !src || !left || !right || !weights) return SRCNN_B200_EINVAL;
+    const int f = (filter >= kNearest && filter <= kBspline) ? filter : kNearest;
+    AxisTable t; build_axis_table(f, dst, src, t);
+    if (t.win > maxwin) return -1;
+    for (unsigned u = 0; u < dst; u++) {
+        left[u] = t.left[u]; right[u] = t.right[u];
+        for (int i = 0; i < maxwin; i++) weights[(size_t)u * maxwin + i] = i < t.win ? t.w[(size_t)u * t.win + i] : 0.0;
+    }
+    return t.win;
+}
+
+} // extern "C"

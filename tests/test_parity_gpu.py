@@ -1,0 +1,273 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI / the C++ drop-in API, against the oracle.
+
+Two arithmetic modes of the fused convolution are checked:
+  exact  (SRCNN_B200_CONV_EXACT)  : FP32 in the reference's summation order  -> every stage and the final image BIT-EXACT
+  tensor (SRCNN_B200_CONV_TENSOR) : tcgen05 FP16 operands / FP32 accumulate  -> north-star tolerance:
+         final 8-bit output within 1 LSB on every channel and PSNR >= 50 dB, conv plane within 1 LSB,
+         network output |dY'| < 1.0; the interpolated Y plane is bit-exact in both modes (tolerance 1e-5 relative).
+"""
+import numpy as np
+import pytest
+from PIL import Image
+
+import libsrcnn_b200 as S
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+G = O.ROOT / "tests" / "golden"
+MODES = [("exact", S.CONV_EXACT), ("tensor", S.CONV_TENSOR)]
+MODE_IDS = [m[0] for m in MODES]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = S.Context(0)
+    yield c
+    c.close()
+
+
+def _check_u8(name, got, want, exact):
+    got = np.asarray(got).reshape(want.shape)
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    if exact:
+        assert diff.max() == 0, "%s: max diff %d, %d px differ" % (name, diff.max(), int((diff > 0).sum()))
+    else:
+        assert diff.max() <= 1, "%s: max diff %d LSB" % (name, diff.max())
+        assert O.psnr(got, want) >= 50.0, "%s: PSNR %.2f dB" % (name, O.psnr(got, want))
+
+
+# ---------------------------------------------------------------------------------------------- single stages
+@pytest.mark.parametrize("d", [3, 4])
+@pytest.mark.parametrize("hw", [(37, 53), (64, 64), (1, 1), (5, 3)])
+def test_stage_color_in_bit_exact(ctx, d, hw):
+    img = O.synth("uniform", hw[0], hw[1], d, 11)
+    for a, b in zip(ctx.color_in(img), O.best().color_in(img)):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("filt", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("shape", [((40, 56), (80, 112)), ((31, 45), (46, 67)), ((64, 64), (40, 30)),
+                                   ((20, 30), (20, 60)), ((20, 30), (45, 30)), ((9, 7), (27, 29)), ((50, 40), (75, 20))])
+def test_stage_resize_bit_exact(ctx, filt, shape):
+    (sh, sw), (dh, dw) = shape
+    p = np.random.default_rng(3).uniform(-20, 280, size=(sh, sw)).astype(np.float32)
+    assert np.array_equal(ctx.resize(p, dw, dh, filt), O.best().resize(p, dw, dh, filt))
+
+
+@pytest.mark.parametrize("hw", [(40, 56), (3, 7), (17, 130), (33, 16), (1, 1), (129, 125)])
+def test_stage_conv_exact_bit_exact(ctx, hw):
+    y = np.random.default_rng(4).uniform(-20, 280, size=hw).astype(np.float32)
+    assert np.array_equal(ctx.conv(y, S.CONV_EXACT), O.best().convs(y))
+
+
+@pytest.mark.parametrize("hw", [(40, 56), (3, 7), (17, 130), (64, 124), (65, 125), (1, 1), (130, 250)])
+@pytest.mark.parametrize("kind", ["uniform", "binary"])
+def test_stage_conv_tensor_within_tolerance(ctx, hw, kind):
+    rng = np.random.default_rng(5)
+    if kind == "uniform":
+        y = rng.uniform(-20, 280, size=hw).astype(np.float32)
+    else:                                   # overshoot range seen with Lanczos-3 on 0/255 noise
+        y = rng.choice(np.array([-117.0, 0.0, 255.0, 372.0], np.float32), size=hw)
+    want = O.best().convs(y)
+    got = ctx.conv(y, S.CONV_TENSOR)
+    assert np.abs(got - want).max() < 1.0
+
+
+@pytest.mark.parametrize("d", [3, 4])
+def test_stage_color_out_bit_exact(ctx, d):
+    rng = np.random.default_rng(6)
+    pl = [rng.uniform(-30, 290, size=(19, 27)).astype(np.float32) for _ in range(d)]
+    pl[0] = np.clip(pl[0], 0, 255)          # the conv III plane is already clamped (reference :519-522)
+    out, conv = ctx.color_out(pl, want_conv=True)
+    assert np.array_equal(out, O.best().color_out(pl))
+    assert np.array_equal(conv, pl[0].astype(np.uint8))
+
+
+# ---------------------------------------------------------------------------------------------- whole path
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+def test_c1_butterfly_golden(ctx, mode):
+    """BASELINE config 1 against the reference's own golden PNGs (reference Pictures/butterfly_srcnn*.png)"""
+    ctx.set_conv_mode(mode[1])
+    src = np.asarray(Image.open(G / "butterfly.png").convert("RGB"))
+    gold = np.asarray(Image.open(G / "butterfly_srcnn.png").convert("RGB"))
+    gconv = np.asarray(Image.open(G / "butterfly_srcnn_convolution.png").convert("L"))
+    rc, out, conv = ctx.process(src, 2.0, S.BICUBIC, False, True)
+    assert rc == 0
+    _check_u8("rgb", out, gold, mode[0] == "exact")
+    _check_u8("conv", conv, gconv, mode[0] == "exact")
+
+
+CASES = [
+    dict(id="c2-like", kind="uniform", h=135, w=240, d=3, m=2.0, f=S.BICUBIC, s=False),
+    dict(id="c3-like-rgba", kind="uniform", h=90, w=160, d=4, m=2.0, f=S.BICUBIC, s=False),
+    dict(id="c4-like-lanczos", kind="uniform", h=128, w=128, d=3, m=2.0, f=S.LANCZOS3, s=False),
+    dict(id="c5-like-bspline-step", kind="uniform", h=72, w=128, d=3, m=1.5, f=S.BSPLINE, s=True),
+    dict(id="binary-lanczos-stress", kind="binary", h=96, w=100, d=3, m=2.0, f=S.LANCZOS3, s=False),
+    dict(id="checker-nearest", kind="checker", h=50, w=70, d=3, m=2.0, f=S.NEAREST, s=False),
+    dict(id="smooth-bilinear-x2.5", kind="smooth", h=41, w=67, d=4, m=2.5, f=S.BILINEAR, s=False),
+    dict(id="step-x3", kind="smooth", h=30, w=44, d=3, m=3.0, f=S.BICUBIC, s=True),
+    dict(id="step-x4-rgba", kind="uniform", h=20, w=28, d=4, m=4.0, f=S.BILINEAR, s=True),
+    dict(id="const0", kind="const0", h=24, w=24, d=3, m=2.0, f=S.BICUBIC, s=False),
+    dict(id="const255", kind="const255", h=24, w=24, d=4, m=2.0, f=S.BICUBIC, s=False),
+    dict(id="tiny-1x1", kind="uniform", h=1, w=1, d=3, m=2.0, f=S.BICUBIC, s=False),
+    dict(id="thin-3x200", kind="uniform", h=3, w=200, d=3, m=2.0, f=S.BICUBIC, s=False),
+    dict(id="downscale-x0.5", kind="smooth", h=64, w=96, d=3, m=0.5, f=S.BICUBIC, s=False),
+    dict(id="bad-filter-id", kind="uniform", h=16, w=16, d=3, m=2.0, f=9, s=False),
+]
+
+
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_process_matches_oracle(ctx, case, mode):
+    ctx.set_conv_mode(mode[1])
+    img = O.synth(case["kind"], case["h"], case["w"], case["d"], 21)
+    rc_o, out_o, conv_o = O.best().process(img, case["m"], case["f"], case["s"])
+    rc, out, conv = ctx.process(img, case["m"], case["f"], case["s"], True)
+    assert rc == rc_o
+    _check_u8("rgb", out, out_o, mode[0] == "exact")
+    _check_u8("conv", conv, conv_o, mode[0] == "exact")
+
+
+@pytest.mark.parametrize("filt", [S.BICUBIC, S.LANCZOS3, S.BSPLINE])
+def test_interpolated_plane_and_network_output(ctx, filt):
+    """the FP32 planes the public API never exposes: interpolated Y within 1e-5 relative (expected 0),
+    tensor-mode network output within 1.0 of the oracle's FP32 plane"""
+    img = O.synth("binary" if filt == S.LANCZOS3 else "uniform", 60, 84, 3, 33)
+    o = O.best()
+    y = o.resize(o.color_in(img)[0], 168, 120, filt)
+    yprime = o.convs(y)
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    ctx.pass_host(img, 2.0, filt)
+    r0, gy = ctx.get_plane(0, (120, 168))
+    assert r0 == 0
+    rel = np.abs(gy - y) / np.maximum(np.abs(y), 1.0)
+    assert rel.max() <= 1e-5
+    assert np.array_equal(gy, y)
+    _, gyp = ctx.get_plane(4, (120, 168))
+    assert np.abs(gyp - yprime).max() < 1.0
+    ctx.set_conv_mode(S.CONV_EXACT)
+    ctx.pass_host(img, 2.0, filt)
+    _, gyp = ctx.get_plane(4, (120, 168))
+    assert np.array_equal(gyp, yprime)
+
+
+def test_dropin_cpp_api_matches_oracle():
+    """ConfigureFilterSRCNN + ProcessSRCNN by their mangled names, new[] ownership, conv plane optional"""
+    img = O.synth("uniform", 48, 64, 4, 8)
+    rc_o, out_o, conv_o = O.best().process(img, 2.0, S.LANCZOS3, False)
+    rc, out, conv = S.process_srcnn(img, 2.0, S.LANCZOS3, False, True)
+    assert rc == rc_o == 0
+    _check_u8("rgb", out, out_o, False)
+    _check_u8("conv", conv, conv_o, False)
+    rc, out2, conv2 = S.process_srcnn(img, 2.0, S.LANCZOS3, False, False)
+    assert rc == 0 and conv2 is None and np.array_equal(out2, out)
+    rc, out3, _ = S.process_srcnn(img, 3.0, S.BICUBIC, True, True)
+    rc_o, out_o3, _ = O.best().process(img, 3.0, S.BICUBIC, True)
+    assert rc == rc_o == 0
+    _check_u8("rgb-step3", out3, out_o3, False)
+    S.lib().ConfigureFilterSRCNN(S.BICUBIC, False)
+
+
+# ---------------------------------------------------------------------------------------------- sharding
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+@pytest.mark.parametrize("nstrips", [2, 3, 8])
+def test_row_strips_equal_full_image(ctx, mode, nstrips):
+    """row-strip shards (6-row halo recomputed) reproduce the single-call result bit for bit"""
+    ctx.set_conv_mode(mode[1])
+    img = O.synth("uniform", 101, 150, 4, 50)
+    full, fconv = ctx.pass_host(img, 2.0, S.BICUBIC, True)
+    oh = full.shape[0]
+    cuts = [round(i * oh / nstrips) for i in range(nstrips + 1)]
+    parts, cparts = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        o, c = ctx.pass_host(img, 2.0, S.BICUBIC, True, rows=(a, b))
+        parts.append(o); cparts.append(c)
+    assert np.array_equal(np.concatenate(parts, 0), full)
+    assert np.array_equal(np.concatenate(cparts, 0), fconv)
+
+
+def test_single_row_strips(ctx):
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    img = O.synth("smooth", 20, 70, 3, 51)
+    full, _ = ctx.pass_host(img, 2.0, S.BSPLINE, False)
+    for r in [0, 1, 5, 20, 38, 39]:
+        o, _ = ctx.pass_host(img, 2.0, S.BSPLINE, False, rows=(r, r + 1))
+        assert np.array_equal(o[0], full[r])
+
+
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+def test_batch_equals_per_frame(ctx, mode):
+    ctx.set_conv_mode(mode[1])
+    frames = np.stack([O.synth("uniform", 48, 48, 3, 60 + i) for i in range(5)])
+    out, conv = ctx.batch(frames, 2.0, S.LANCZOS3, want_conv=True)
+    for i in range(5):
+        o, c = ctx.pass_host(frames[i], 2.0, S.LANCZOS3, True)
+        assert np.array_equal(out[i], o) and np.array_equal(conv[i], c)
+
+
+def test_device_resident_pass_equals_host_pass(ctx):
+    import torch
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    img = O.synth("uniform", 90, 120, 3, 70)
+    want, wconv = ctx.pass_host(img, 2.0, S.BICUBIC, True)
+    d_src = torch.from_numpy(img).cuda()
+    d_out = torch.empty((180, 240, 3), dtype=torch.uint8, device="cuda")
+    d_conv = torch.empty((180, 240), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.pass_device(d_src.data_ptr(), 120, 90, 3, 2.0, S.BICUBIC, d_out.data_ptr(), d_conv.data_ptr())
+    ctx.sync()
+    assert np.array_equal(d_out.cpu().numpy(), want) and np.array_equal(d_conv.cpu().numpy(), wconv)
+
+
+# ---------------------------------------------------------------------------------------------- full sizes
+def test_c2_full_size_against_oracle(ctx):
+    """BASELINE config 2 at full size: 1920x1080 RGB x2 bicubic -> 3840x2160, against the oracle (CPU, ~10-30 s)"""
+    img = O.synth("uniform", 1080, 1920, 3, 42)
+    rc_o, out_o, conv_o = O.best().process(img, 2.0, S.BICUBIC, False)
+    assert rc_o == 0
+    out_o = out_o.reshape(2160, 3840, 3)
+    ctx.set_conv_mode(S.CONV_EXACT)
+    out, conv = ctx.pass_host(img, 2.0, S.BICUBIC, True)
+    _check_u8("exact rgb", out, out_o, True)
+    _check_u8("exact conv", conv, conv_o.reshape(2160, 3840), True)
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    out, conv = ctx.pass_host(img, 2.0, S.BICUBIC, True)
+    _check_u8("tensor rgb", out, out_o, False)
+    _check_u8("tensor conv", conv, conv_o.reshape(2160, 3840), False)
+
+
+FULL = [
+    dict(id="c3-7680x4320-rgba", h=4320, w=7680, d=4, m=2.0, f=S.BICUBIC, seed=43, strips=8),
+    dict(id="c4-frame-512-lanczos", h=512, w=512, d=3, m=2.0, f=S.LANCZOS3, seed=44, strips=2),
+    dict(id="c5-3840x2160-x1.5-bspline", h=2160, w=3840, d=3, m=1.5, f=S.BSPLINE, seed=45, strips=4),
+]
+
+
+@pytest.mark.parametrize("case", FULL, ids=[c["id"] for c in FULL])
+def test_full_size_properties(ctx, case):
+    """BASELINE configs 3-5 at full size through size-independent properties:
+    (a) tensor mode within 1 LSB / 50 dB of the bit-exact mode (itself pinned to the oracle at small sizes and at C2);
+    (b) row-strip shards concatenate to the single-call result bit for bit;
+    (c) an oracle run on a crop of the source agrees with the interior of the same region (all stages are local)."""
+    img = O.synth("uniform", case["h"], case["w"], case["d"], case["seed"])
+    ow, oh = S.output_dims(case["w"], case["h"], case["m"])
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    full, fconv = ctx.pass_host(img, case["m"], case["f"], True)
+    # (b)
+    cuts = [round(i * oh / case["strips"]) for i in range(case["strips"] + 1)]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        o, c = ctx.pass_host(img, case["m"], case["f"], True, rows=(a, b))
+        assert np.array_equal(o, full[a:b]) and np.array_equal(c, fconv[a:b])
+    # (a)
+    ctx.set_conv_mode(S.CONV_EXACT)
+    ex, exconv = ctx.pass_host(img, case["m"], case["f"], True)
+    _check_u8("tensor-vs-exact rgb", full, ex, False)
+    _check_u8("tensor-vs-exact conv", fconv, exconv, False)
+    # (c) top-left crop: source 96x128 -> compare the region at least 16 output px away from the crop's cut edges
+    ch, cw = min(96, case["h"]), min(128, case["w"])
+    rc, o_crop, _ = O.best().process(img[:ch, :cw], case["m"], case["f"], False)
+    cow, coh = S.output_dims(cw, ch, case["m"])
+    o_crop = o_crop.reshape(coh, cow, case["d"])
+    ih = coh - 16 if ch < case["h"] else coh
+    iw = cow - 16 if cw < case["w"] else cow
+    assert np.array_equal(ex[:ih, :iw], o_crop[:ih, :iw])
