@@ -10,6 +10,9 @@
  * Environment knobs (the header stays untouched):
  *   SRCNN_B200_DEVICE=<n>     CUDA device of the process-wide context (default 0)
  *   SRCNN_B200_CONV=exact     use the bit-exact FP32 CUDA-core convolution instead of the tcgen05 kernel
+ *   SRCNN_B200_CHAIN=tensor   step-scale chains (factor > 2): run the intermediate x2 passes on the tcgen05 kernel too
+ *                             (default: intermediates use the bit-exact kernel so the chained result stays within
+ *                             1 LSB of the reference; only the last pass uses the tensor cores)
  */
 #include "../../include/libsrcnn.h"
 #include "../../include/srcnn_b200.h"

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <tuple>
@@ -75,6 +76,7 @@ struct srcnn_b200_ctx {
     std::map<std::tuple<int, unsigned, unsigned>, TableDev*> tables;
     ConvTcState* tc = nullptr;
     int conv_mode = SRCNN_B200_CONV_TENSOR;
+    bool chain_tensor = false;      /* step-scale chains: tensor kernel also for the intermediate passes */
     bool timing = false;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
@@ -225,7 +227,7 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, bool src_i
     /* 4./5. fused conv I+II+III on the Y plane */
     if (ctx->conv_mode == SRCNN_B200_CONV_TENSOR) {
         const Y16Geom g = y16_geometry(p.ow, orows);
-        CK(ctx->y16.ensure((size_t)g.pitch * g.rows * sizeof(__half)));
+        CK(ctx->y16.ensure((size_t)2 * g.pitch * g.rows * sizeof(__half)));   /* planes E and O */
         launch_pack_y16(P_dst, p.ow, p.oh, p.e0, static_cast<__half*>(ctx->y16.p), g, p.r0, s); ctx->launches++;
         st.mark();
         if (launch_conv_tc(ctx->tc, static_cast<const __half*>(ctx->y16.p), g, p.ow, p.oh, Yp, p.r0, p.r1,
@@ -293,6 +295,7 @@ int srcnn_b200_create(int device, srcnn_b200_ctx** out)
     }
     srcnn_b200_ctx* ctx = new srcnn_b200_ctx;
     ctx->device = device; ctx->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("SRCNN_B200_CHAIN")) ctx->chain_tensor = (strcmp(e, "tensor") == 0);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -480,12 +483,19 @@ int srcnn_b200_process_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w,
         rc = make_plan(cw, ch, d, f[i], filter, 0, p.oh, p);
         if (rc) return rc;
         const bool last = (i + 1 == n);
+        /* An intermediate pass feeds the next one through an 8-bit image: a 1-LSB difference there would be
+         * amplified by the following pass, so unless asked otherwise intermediates use the bit-exact kernel and
+         * only the last pass (whose output is what the 1-LSB criterion is about) uses the tensor-core kernel. */
+        const int saved_mode = ctx->conv_mode;
+        if (!last && !ctx->chain_tensor) ctx->conv_mode = SRCNN_B200_CONV_EXACT;
         const size_t ob = (size_t)p.ow * p.oh * d;
-        CK(ctx->chain[cur ^ 1].ensure(ob));
-        if (last && conv) CK(ctx->conv8[0].ensure((size_t)p.ow * p.oh));
+        { cudaError_t e1 = ctx->chain[cur ^ 1].ensure(ob);
+          if (e1 == cudaSuccess && last && conv) e1 = ctx->conv8[0].ensure((size_t)p.ow * p.oh);
+          if (e1 != cudaSuccess) { ctx->conv_mode = saved_mode; return fail_cuda(ctx, e1, "chain buffers"); } }
         rc = run_pass(ctx, p, static_cast<const uint8_t*>(ctx->chain[cur].p), true,
                       static_cast<uint8_t*>(ctx->chain[cur ^ 1].p),
                       (last && conv) ? static_cast<uint8_t*>(ctx->conv8[0].p) : nullptr);
+        ctx->conv_mode = saved_mode;
         if (rc) return rc;
         cur ^= 1; cw = p.ow; ch = p.oh;
     }
@@ -632,7 +642,7 @@ int srcnn_b200_stage_conv(srcnn_b200_ctx* ctx, const float* y, unsigned w, unsig
         launch_conv_exact(Y, w, h, 0, h, O, 0, h, s); ctx->launches++;
     } else if (mode == SRCNN_B200_CONV_TENSOR) {
         const Y16Geom g = y16_geometry(w, h);
-        CK(ctx->y16.ensure((size_t)g.pitch * g.rows * sizeof(__half)));
+        CK(ctx->y16.ensure((size_t)2 * g.pitch * g.rows * sizeof(__half)));   /* planes E and O */
         launch_pack_y16(Y, w, h, 0, static_cast<__half*>(ctx->y16.p), g, 0, s); ctx->launches++;
         if (launch_conv_tc(ctx->tc, static_cast<const __half*>(ctx->y16.p), g, w, h, O, 0, h, ctx->num_sms, s)) {
             ctx->err = std::string("conv_tc: ") + conv_tc_error(ctx->tc);
