@@ -1,26 +1,31 @@
-/* Fused conv I + II + III on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only -- the product path.
+/* Fused conv I + II + III on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a only -- the product path.
  *
  * Replaces the reference's three OpenMP stages convolution99 x64 -> convolution11 x32 -> convolution55
  * (src/libsrcnn.cpp:350-529, drivers :783-846).  The 64- and 32-channel intermediates never leave the SM.
  *
- * Mapping.  A CTA owns a band of 128 adjacent image columns (124 output columns + 2x2 halo for conv III) and walks
- * down a row segment; TMEM lane t = thread t = image column c0 + t.  For every image row q the three layers are three
- * chained M=128 implicit GEMMs whose A operand lives in TENSOR MEMORY (written by tcgen05.st, lane = pixel,
+ * Mapping.  A persistent CTA (one per SM) owns bands of 128 adjacent image columns (124 output columns + 2x2 halo for
+ * conv III) and walks down row segments; TMEM lane t = image column c0 + t.  For every image row the three layers are
+ * three chained M=128 implicit GEMMs whose A operand lives in TENSOR MEMORY (written by tcgen05.st: lane = pixel,
  * column = two packed FP16 K elements) and whose B operand (the weights) sits in shared memory in the canonical
  * K-major no-swizzle core-matrix layout:
  *
- *   conv I  : A1[px][k = 10*i + j] = Y16(q-4+i, c-4+j)   K = 96 (81 taps, the j = 9 column and k >= 92 carry zero
- *             weights, k = 90/91 are constant 1.0 inputs whose weights are the bias split hi/lo)          N = 64
+ *   conv I  : A1[px][k = 10*i + j] = Y16(q-4+i, c-4+j)   K = 96 (81 taps; the j = 9 column and k >= 92 carry zero
+ *             weights; k = 90/91 are constant 1.0 inputs whose weights are the bias split hi/lo)          N = 64
  *             each thread keeps its 9x10 window in registers and rolls it down one row per step, so building the
- *             im2col operand costs five 32-bit loads per pixel instead of 81
+ *             im2col operand costs six 32-bit shared loads per pixel instead of 81
  *   conv II : A2[px][k] = fp16(ReLU(D1[px][k]))          K = 64, N = 32   (bias + ReLU in the FP32 epilogue)
  *   conv III: "taps as N": Z[px][tap] = sum_ch A3[px][ch] * W3[ch][tap]   K = 32, N = 32 (25 used); the 5x5 spatial
  *             gather out(r,c) = sum_{dy,dx} Z[(r+dy, c+dx)][tap(dy,dx)] is then 25 FP32 adds per pixel: the dy part
  *             accumulates in registers while the rows stream by, the dx part crosses lanes through shared memory.
  *
+ * Warp specialisation (20 warps): TMA producer (Y16 row chunks -> 4-stage smem ring), MMA issuer (one thread),
+ * TMEM allocator, and four 4-warp groups -- im2col, epilogue I, epilogue II, gather/store -- chained by mbarriers
+ * with every TMEM operand / accumulator region double-buffered, so the tensor pipe works on row n while the groups
+ * prepare row n+1 and drain rows n-1, n-2.
+ *
  * Border semantics follow the reference exactly: conv I clamps Y coordinates (the Y16 plane is replicate-padded by
  * the pack kernel), conv III clamps the coordinates of the conv II plane itself (src/libsrcnn.cpp:461-491), which
- * here becomes a clamp on the row/lane index of Z in the gather.
+ * here becomes a clamp on the row / lane index of Z in the gather.
  *
  * Arithmetic: FP16 operands (round-to-nearest), FP32 accumulation in TMEM, FP32 epilogues.  SURVEY.md 7.4 shows this
  * keeps |dY'| < 1 (final 8-bit output within 1 LSB); tests/test_parity_gpu.py asserts it against the oracle.
@@ -28,6 +33,7 @@
 #include "kernels.h"
 #include "srcnn_weights_data.h"
 
+#include <cuda.h>
 #include <string>
 #include <vector>
 #include <cstring>
@@ -42,8 +48,22 @@ constexpr int K3 = 32, N3 = 32;     /* conv III GEMM (taps as N) */
 constexpr int B1_BYTES = N1 * K1 * 2, B2_BYTES = N2 * K2 * 2, B3_BYTES = N3 * K3 * 2;
 constexpr int WIMG_BYTES = B1_BYTES + B2_BYTES + B3_BYTES;
 
-/* TMEM columns inside the CTA's 256-column allocation */
-constexpr uint32_t D1_COL = 0, D2_COL = 64, D3_COL = 96, A1_COL = 128, A2_COL = 192, A3_COL = 224, TMEM_COLS = 256;
+/* TMEM columns (512 allocated); every region double-buffered: index b = row & 1 */
+constexpr uint32_t D1_COL = 0, D2_COL = 128, D3_COL = 192, A1_COL = 256, A2_COL = 352, A3_COL = 416;
+constexpr uint32_t D1_STR = 64, D2_STR = 32, D3_STR = 32, A1_STR = 48, A2_STR = 32, A3_STR = 16;
+
+/* Y16 staging ring */
+constexpr int CH_ROWS = 8, BOX_W = 144, NST = 4;
+constexpr int CH_BYTES = CH_ROWS * BOX_W * 2;
+
+/* warp roles */
+constexpr int W_TMA = 0, W_MMA1 = 1, W_ALLOC = 2, W_MMA23 = 3, W_IM2COL = 4, W_E1 = 8, W_E2 = 12, W_E3 = 16, NWARPS = 20;
+
+/* barrier indices.  M?_DONE[b] fires when the MMAs of layer ? for a row with parity b have completed: it both frees the
+ * A operand region for the producer group and publishes the accumulator to the consumer group. */
+enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + 2, D1_EMPTY = M1_DONE + 2,
+       A2_FULL = D1_EMPTY + 2, M2_DONE = A2_FULL + 2, D2_EMPTY = M2_DONE + 2,
+       A3_FULL = D2_EMPTY + 2, M3_DONE = A3_FULL + 2, D3_EMPTY = M3_DONE + 2, NBAR = D3_EMPTY + 2 };
 
 __constant__ float cBias2[32];
 __constant__ float cBias3;
@@ -71,11 +91,28 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
                  "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -98,16 +135,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* r)
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(addr) : "memory");
 }
-__device__ __forceinline__ uint32_t pack_relu_h2(float lo, float hi)
+/* two FP32 -> packed FP16x2 with ReLU in one instruction; `lo` lands in the low half (even K index) */
+__device__ __forceinline__ uint32_t cvt_relu_h2(float lo, float hi)
 {
-    const __half2 h = __floats2half2_rn(fmaxf(lo, 0.f), fmaxf(hi, 0.f));      /* .x = low 16 bits = even K index */
-    return *reinterpret_cast<const uint32_t*>(&h);
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+/* warp-uniform code, one elected lane issues (keeps descriptors / addresses in uniform registers) */
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+/* one lane per warp signals for the whole warp (barrier counts are 4 = warps per group) */
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane)
+{
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
 }
 
 /* ---------------------------------------------------------------- the kernel */
 struct TcParams {
-    const __half* y16;          /* plane E; plane O (= E shifted left by one half) follows at +plane_halves */
-    size_t plane_halves;
     int pitch, y16_rows;
     int dw, dh;
     float* out;                 /* rows [row0,row1) x dw */
@@ -116,25 +166,46 @@ struct TcParams {
     const unsigned char* wimg;  /* B1 | B2 | B3 operand images */
 };
 
-__global__ void __launch_bounds__(128, 2)
-conv_tc_kernel(const TcParams p)
+struct Unit { int band, ra, rb, nrows; };
+__device__ __forceinline__ Unit unit_of(const TcParams& p, int u)
 {
+    Unit x;
+    x.band = u % p.bands;
+    const int seg = u / p.bands;
+    x.ra = p.row0 + seg * p.seg_rows;
+    x.rb = min(x.ra + p.seg_rows, p.row1);
+    x.nrows = x.rb - x.ra + 4;              /* intermediate rows q = ra-2 .. rb+1 */
+    return x;
+}
+
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
+{
+    __shared__ __align__(1024) unsigned char sY[NST * CH_BYTES];
     __shared__ __align__(128) unsigned char sW[WIMG_BYTES];
     __shared__ __align__(16) float sP[2][5][128];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[NBAR];
     __shared__ uint32_t s_tmem;
 
-    const int t = threadIdx.x, warp = t >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    /* one-time setup: weights -> smem (generic proxy, then made visible to the async proxy), barrier, TMEM */
-    for (int i = t; i < WIMG_BYTES / 16; i += 128)
+    /* one-time setup: weights -> smem (generic proxy, then made visible to the async proxy), barriers, TMEM */
+    for (int i = tid; i < WIMG_BYTES / 16; i += NWARPS * 32)
         reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
-    if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar)));
+    if (tid == 0) {
+        for (int i = 0; i < NST; i++) { mbar_init(smem_u32(&s_bar[Y_FULL + i]), 1); mbar_init(smem_u32(&s_bar[Y_EMPTY + i]), 4); }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(smem_u32(&s_bar[A1_FULL + b]), 4); mbar_init(smem_u32(&s_bar[M1_DONE + b]), 1);
+            mbar_init(smem_u32(&s_bar[D1_EMPTY + b]), 4);
+            mbar_init(smem_u32(&s_bar[A2_FULL + b]), 4); mbar_init(smem_u32(&s_bar[M2_DONE + b]), 1);
+            mbar_init(smem_u32(&s_bar[D2_EMPTY + b]), 4);
+            mbar_init(smem_u32(&s_bar[A3_FULL + b]), 4); mbar_init(smem_u32(&s_bar[M3_DONE + b]), 1);
+            mbar_init(smem_u32(&s_bar[D3_EMPTY + b]), 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(&s_tmem)) : "memory");
+    if (warp == W_ALLOC) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -143,199 +214,283 @@ conv_tc_kernel(const TcParams p)
     tc_fence_after();
 
     const uint32_t tmem = s_tmem;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);     /* this warp's 32 TMEM lanes */
-    const uint32_t bar = smem_u32(&s_bar);
-    const uint32_t sB1 = smem_u32(sW), sB2 = sB1 + B1_BYTES, sB3 = sB2 + B2_BYTES;
-    uint32_t phase = 0;
-
+    const uint32_t bar0 = smem_u32(&s_bar[0]);
+    auto BAR = [&](int i) -> uint32_t { return bar0 + 8u * (uint32_t)i; };
     const int units = p.bands * p.nsegs;
-    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-        const int band = unit % p.bands, seg = unit / p.bands;
-        const int ra = p.row0 + seg * p.seg_rows;
-        const int rb = min(ra + p.seg_rows, p.row1);
-        const int c0 = band * kBandCols - 2;                 /* image column of lane 0 */
-        const int c  = c0 + t;
-        /* this thread's 10-half window starts at plane column c - 4 + 8; odd lanes read the shifted plane */
-        const __half* ybase = p.y16 + ((t & 1) ? p.plane_halves : 0) + (band * kBandCols + 2 + t - (t & 1));
-        auto load_row = [&](int g, uint32_t* w5) {            /* g = global image row (may be outside: plane is padded) */
-            int yr = g - (p.row0 - kHaloRows);
-            yr = yr < 0 ? 0 : (yr > p.y16_rows - 1 ? p.y16_rows - 1 : yr);
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(ybase + (size_t)yr * p.pitch);
-            #pragma unroll
-            for (int j = 0; j < 5; j++) w5[j] = __ldg(src + j);
-        };
 
-        uint32_t W[9][5];                                     /* rows q-4 .. q+4 of the window, 2 halves per word */
-        const int q0 = ra - 2, q1 = rb + 1;                   /* intermediate rows this unit evaluates */
-        #pragma unroll
-        for (int i = 0; i < 9; i++) load_row(q0 - 4 + i, W[i]);
-
-        float acc[5][5];                                      /* acc[j][dx]: partial of output row q-2+j, column c-(dx-2) */
-        #pragma unroll
-        for (int j = 0; j < 5; j++)
-            #pragma unroll
-            for (int d = 0; d < 5; d++) acc[j][d] = 0.f;
-
-        for (int q = q0; q <= q1; q++) {
-            uint32_t nxt[5];
-            load_row(q + 5, nxt);                             /* prefetch next step's new row */
-
-            if (q >= 0 && q < p.dh) {
-                /* ---- conv I: im2col operand -> TMEM (48 columns = 96 halves) */
-                {
-                    uint32_t r[16];
-                    #pragma unroll
-                    for (int m = 0; m < 16; m++) r[m] = W[m / 5][m % 5];
-                    tmem_st16(lane_base + A1_COL, r);
-                    #pragma unroll
-                    for (int m = 0; m < 16; m++) r[m] = W[(m + 16) / 5][(m + 16) % 5];
-                    tmem_st16(lane_base + A1_COL + 16, r);
-                    #pragma unroll
-                    for (int m = 0; m < 13; m++) r[m] = W[(m + 32) / 5][(m + 32) % 5];
-                    r[13] = 0x3C003C00u;                      /* k = 90, 91: constant 1.0 (bias inputs) */
-                    r[14] = 0u; r[15] = 0u;
-                    tmem_st16(lane_base + A1_COL + 32, r);
+    if (warp == W_TMA) {
+        /* ===================== TMA producer: Y16 rows of the current unit, 8-row chunks ===================== */
+        uint32_t ck = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const Unit un = unit_of(p, u);
+            const int x0 = (un.band * kBandCols + 2) & ~7;            /* 16 B aligned box origin */
+            const int yr0 = un.ra - p.row0;                           /* plane row of image row ra-6 */
+            const int nch = (un.nrows + 8 + CH_ROWS - 1) / CH_ROWS;
+            for (int j = 0; j < nch; j++, ck++) {
+                const uint32_t s = ck % NST, k = ck / NST;
+                mbar_wait(BAR(Y_EMPTY + s), (k & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(BAR(Y_FULL + s), CH_BYTES);
+                    tma_load_2d(smem_u32(sY) + s * CH_BYTES, &ymap, x0, yr0 + j * CH_ROWS, BAR(Y_FULL + s));
                 }
-                tmem_wait_st();
-                tc_fence_before();
-                __syncthreads();
-                if (t == 0) {
-                    tc_fence_after();
-                    #pragma unroll
-                    for (int s = 0; s < K1 / 16; s++)
-                        umma_ts(tmem + D1_COL, tmem + A1_COL + 8 * s, umma_desc(sB1 + 256 * s, 128, (K1 / 8) * 128),
-                                umma_idesc(N1), s > 0);
-                    umma_commit(bar);
-                }
-                mbar_wait(bar, phase); phase ^= 1;
-                tc_fence_after();
-
-                /* ---- epilogue I: ReLU (bias already inside the GEMM), FP16, -> A2 */
-                {
-                    uint32_t v[32], r[16];
-                    tmem_ld32(lane_base + D1_COL, v);
-                    tmem_wait_ld();
-                    #pragma unroll
-                    for (int m = 0; m < 16; m++) r[m] = pack_relu_h2(__uint_as_float(v[2 * m]), __uint_as_float(v[2 * m + 1]));
-                    tmem_st16(lane_base + A2_COL, r);
-                    tmem_ld32(lane_base + D1_COL + 32, v);
-                    tmem_wait_ld();
-                    #pragma unroll
-                    for (int m = 0; m < 16; m++) r[m] = pack_relu_h2(__uint_as_float(v[2 * m]), __uint_as_float(v[2 * m + 1]));
-                    tmem_st16(lane_base + A2_COL + 16, r);
-                }
-                tmem_wait_st();
-                tc_fence_before();
-                __syncthreads();
-                if (t == 0) {
-                    tc_fence_after();
-                    #pragma unroll
-                    for (int s = 0; s < K2 / 16; s++)
-                        umma_ts(tmem + D2_COL, tmem + A2_COL + 8 * s, umma_desc(sB2 + 256 * s, 128, (K2 / 8) * 128),
-                                umma_idesc(N2), s > 0);
-                    umma_commit(bar);
-                }
-                mbar_wait(bar, phase); phase ^= 1;
-                tc_fence_after();
-
-                /* ---- epilogue II: + bias, ReLU, FP16, -> A3 */
-                {
-                    uint32_t v[32], r[16];
-                    tmem_ld32(lane_base + D2_COL, v);
-                    tmem_wait_ld();
-                    #pragma unroll
-                    for (int m = 0; m < 16; m++)
-                        r[m] = pack_relu_h2(__uint_as_float(v[2 * m]) + cBias2[2 * m], __uint_as_float(v[2 * m + 1]) + cBias2[2 * m + 1]);
-                    tmem_st16(lane_base + A3_COL, r);
-                }
-                tmem_wait_st();
-                tc_fence_before();
-                __syncthreads();
-                if (t == 0) {
-                    tc_fence_after();
-                    #pragma unroll
-                    for (int s = 0; s < K3 / 16; s++)
-                        umma_ts(tmem + D3_COL, tmem + A3_COL + 8 * s, umma_desc(sB3 + 256 * s, 128, (K3 / 8) * 128),
-                                umma_idesc(N3), s > 0);
-                    umma_commit(bar);
-                }
-                mbar_wait(bar, phase); phase ^= 1;
-                tc_fence_after();
-
-                /* ---- conv III gather, dy part: Z row q feeds output rows q-2 .. q+2 */
-                {
-                    uint32_t z[32];
-                    tmem_ld32(lane_base + D3_COL, z);
-                    tmem_wait_ld();
-                    if (q != 0 && q != p.dh - 1) {
-                        #pragma unroll
-                        for (int j = 0; j < 5; j++)
-                            #pragma unroll
-                            for (int d = 0; d < 5; d++) acc[j][d] += __uint_as_float(z[(4 - j) * 5 + d]);
-                    } else {
-                        /* first / last image row: also stands in for the clamped rows above / below it */
-                        #pragma unroll
-                        for (int j = 0; j < 5; j++)
-                            #pragma unroll
-                            for (int dyi = 0; dyi < 5; dyi++) {
-                                const bool on = (dyi == 4 - j) || (q == 0 && dyi < 4 - j) || (q == p.dh - 1 && dyi > 4 - j);
-                                if (on) {
-                                    #pragma unroll
-                                    for (int d = 0; d < 5; d++) acc[j][d] += __uint_as_float(z[dyi * 5 + d]);
-                                }
-                            }
-                    }
-                }
+                __syncwarp();
             }
-
-            /* ---- output row r = q - 2 is complete: dx part of the gather across lanes, bias, clamp, store */
-            const int r = q - 2;
-            if (r >= ra && r < rb) {                          /* uniform over the CTA */
-                float (*P)[128] = sP[q & 1];
-                #pragma unroll
-                for (int d = 0; d < 5; d++) P[d][t] = acc[0][d];
-                __syncthreads();
-                if (t >= 2 && t < 126 && c < p.dw) {
-                    float o = cBias3;
-                    #pragma unroll
-                    for (int d = 0; d < 5; d++) {
-                        int cc = c + d - 2;
-                        cc = cc < 0 ? 0 : (cc > p.dw - 1 ? p.dw - 1 : cc);
-                        o += P[d][cc - c0];
-                    }
-                    o = fminf(fmaxf(o, 0.f), 255.f);
-                    p.out[(size_t)(r - p.row0) * p.dw + c] = o;
-                }
-            }
-            /* roll the window and the accumulators down one row */
-            #pragma unroll
-            for (int j = 0; j < 4; j++)
-                #pragma unroll
-                for (int d = 0; d < 5; d++) acc[j][d] = acc[j + 1][d];
-            #pragma unroll
-            for (int d = 0; d < 5; d++) acc[4][d] = 0.f;
-            #pragma unroll
-            for (int i = 0; i < 8; i++)
-                #pragma unroll
-                for (int j = 0; j < 5; j++) W[i][j] = W[i + 1][j];
-            #pragma unroll
-            for (int j = 0; j < 5; j++) W[8][j] = nxt[j];
         }
-        __syncthreads();                                      /* sP reuse across units */
+    } else if (warp == W_MMA1) {
+        /* ===================== MMA issuer, conv I.  Rows of all units form one continuous stream. ============
+         * Warp-uniform control flow; one elected lane issues. */
+        int total = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) total += unit_of(p, u).nrows;
+        const uint64_t db1 = umma_desc(smem_u32(sW), 128, (K1 / 8) * 128);
+        for (int g = 0; g < total; g++) {
+            const uint32_t b = g & 1, ph = (g >> 1) & 1;
+            mbar_wait(BAR(A1_FULL + b), ph);
+            mbar_wait(BAR(D1_EMPTY + b), ph ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = tmem + D1_COL + b * D1_STR, a = tmem + A1_COL + b * A1_STR;
+                #pragma unroll
+                for (int s = 0; s < K1 / 16; s++) umma_ts(d, a + 8 * s, db1 + 16 * s, umma_idesc(N1), s > 0);
+                umma_commit(BAR(M1_DONE + b));
+            }
+            __syncwarp();
+        }
+    } else if (warp == W_MMA23) {
+        /* ===================== MMA issuer, conv II (row g) and conv III (row g-1) =========================== */
+        int total = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) total += unit_of(p, u).nrows;
+        const uint64_t db2 = umma_desc(smem_u32(sW) + B1_BYTES, 128, (K2 / 8) * 128);
+        const uint64_t db3 = umma_desc(smem_u32(sW) + B1_BYTES + B2_BYTES, 128, (K3 / 8) * 128);
+        for (int g = 0; g < total + 1; g++) {
+            if (g < total) {
+                const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                mbar_wait(BAR(A2_FULL + b), ph);
+                mbar_wait(BAR(D2_EMPTY + b), ph ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d = tmem + D2_COL + b * D2_STR, a = tmem + A2_COL + b * A2_STR;
+                    #pragma unroll
+                    for (int s = 0; s < K2 / 16; s++) umma_ts(d, a + 8 * s, db2 + 16 * s, umma_idesc(N2), s > 0);
+                    umma_commit(BAR(M2_DONE + b));
+                }
+                __syncwarp();
+            }
+            if (g >= 1) {
+                const int m = g - 1; const uint32_t b = m & 1, ph = (m >> 1) & 1;
+                mbar_wait(BAR(A3_FULL + b), ph);
+                mbar_wait(BAR(D3_EMPTY + b), ph ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d = tmem + D3_COL + b * D3_STR, a = tmem + A3_COL + b * A3_STR;
+                    #pragma unroll
+                    for (int s = 0; s < K3 / 16; s++) umma_ts(d, a + 8 * s, db3 + 16 * s, umma_idesc(N3), s > 0);
+                    umma_commit(BAR(M3_DONE + b));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= W_IM2COL && warp < W_IM2COL + 4) {
+        /* ===================== im2col: smem Y16 ring -> rolling 9x10 register window -> A1 in TMEM ========== */
+        const int t = (warp - W_IM2COL) * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t it = 0, ck = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const Unit un = unit_of(p, u);
+            const int hw = ((un.band * kBandCols + 2) & 7) + t;       /* half offset of this lane's window in the box */
+            const uint32_t woff = (uint32_t)(hw >> 1) * 4u, sh = (uint32_t)(hw & 1) * 16u;
+            const int last_rho = un.nrows + 7;
+            uint32_t W[9][5];
+            auto fetch = [&](int rho, uint32_t* w5) {
+                const uint32_t c = ck + (uint32_t)(rho / CH_ROWS), s = c % NST;
+                if ((rho % CH_ROWS) == 0) mbar_wait(BAR(Y_FULL + s), (c / NST) & 1);
+                const uint32_t a = smem_u32(sY) + s * CH_BYTES + (uint32_t)(rho % CH_ROWS) * (BOX_W * 2) + woff;
+                uint32_t x[6];
+                #pragma unroll
+                for (int j = 0; j < 6; j++) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[j]) : "r"(a + 4u * j));
+                #pragma unroll
+                for (int j = 0; j < 5; j++) w5[j] = __funnelshift_r(x[j], x[j + 1], sh);
+                if ((rho % CH_ROWS) == CH_ROWS - 1 || rho == last_rho) warp_arrive(BAR(Y_EMPTY + s), lane);
+            };
+            #pragma unroll
+            for (int i = 0; i < 8; i++) fetch(i, W[i]);
+            for (int n0 = 0; n0 < un.nrows; n0 += 9) {
+                #pragma unroll
+                for (int uu = 0; uu < 9; uu++) {
+                    const int n = n0 + uu;
+                    if (n < un.nrows) {
+                        fetch(n + 8, W[(uu + 8) % 9]);
+                        const uint32_t b = it & 1, ph = (it >> 1) & 1;
+                        mbar_wait(BAR(M1_DONE + b), ph ^ 1);
+                        tc_fence_after();
+                        const uint32_t dst = lane_base + A1_COL + b * A1_STR;
+                        uint32_t r[16];
+                        #pragma unroll
+                        for (int m = 0; m < 16; m++) r[m] = W[(uu + m / 5) % 9][m % 5];
+                        tmem_st16(dst, r);
+                        #pragma unroll
+                        for (int m = 0; m < 16; m++) r[m] = W[(uu + (m + 16) / 5) % 9][(m + 16) % 5];
+                        tmem_st16(dst + 16, r);
+                        #pragma unroll
+                        for (int m = 0; m < 13; m++) r[m] = W[(uu + (m + 32) / 5) % 9][(m + 32) % 5];
+                        r[13] = 0x3C003C00u;                  /* k = 90, 91: constant 1.0 (bias inputs) */
+                        r[14] = 0u; r[15] = 0u;
+                        tmem_st16(dst + 32, r);
+                        tmem_wait_st();
+                        tc_fence_before();
+                        warp_arrive(BAR(A1_FULL + b), lane);
+                        it++;
+                    }
+                }
+            }
+            ck += (uint32_t)((un.nrows + 8 + CH_ROWS - 1) / CH_ROWS);
+        }
+    } else if (warp >= W_E1 && warp < W_E1 + 4) {
+        /* ===================== epilogue I: D1 -> ReLU -> FP16 -> A2 (bias is already inside the GEMM) ======== */
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int nrows = unit_of(p, u).nrows;
+            for (int n = 0; n < nrows; n++, it++) {
+                const uint32_t b = it & 1, ph = (it >> 1) & 1;
+                uint32_t v[32], r0[16], r1[16];
+                mbar_wait(BAR(M1_DONE + b), ph);
+                tc_fence_after();
+                tmem_ld32(lane_base + D1_COL + b * D1_STR, v);
+                tmem_wait_ld();
+                #pragma unroll
+                for (int m = 0; m < 16; m++) r0[m] = cvt_relu_h2(__uint_as_float(v[2 * m]), __uint_as_float(v[2 * m + 1]));
+                tmem_ld32(lane_base + D1_COL + b * D1_STR + 32, v);
+                tmem_wait_ld();
+                tc_fence_before();
+                warp_arrive(BAR(D1_EMPTY + b), lane);
+                #pragma unroll
+                for (int m = 0; m < 16; m++) r1[m] = cvt_relu_h2(__uint_as_float(v[2 * m]), __uint_as_float(v[2 * m + 1]));
+                mbar_wait(BAR(M2_DONE + b), ph ^ 1);
+                tc_fence_after();
+                tmem_st16(lane_base + A2_COL + b * A2_STR, r0);
+                tmem_st16(lane_base + A2_COL + b * A2_STR + 16, r1);
+                tmem_wait_st();
+                tc_fence_before();
+                warp_arrive(BAR(A2_FULL + b), lane);
+            }
+        }
+    } else if (warp >= W_E2 && warp < W_E2 + 4) {
+        /* ===================== epilogue II: D2 + bias -> ReLU -> FP16 -> A3 ================================= */
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int nrows = unit_of(p, u).nrows;
+            for (int n = 0; n < nrows; n++, it++) {
+                const uint32_t b = it & 1, ph = (it >> 1) & 1;
+                uint32_t v[32], r[16];
+                mbar_wait(BAR(M2_DONE + b), ph);
+                tc_fence_after();
+                tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
+                tmem_wait_ld();
+                tc_fence_before();
+                warp_arrive(BAR(D2_EMPTY + b), lane);
+                #pragma unroll
+                for (int m = 0; m < 16; m++)
+                    r[m] = cvt_relu_h2(__uint_as_float(v[2 * m]) + cBias2[2 * m], __uint_as_float(v[2 * m + 1]) + cBias2[2 * m + 1]);
+                mbar_wait(BAR(M3_DONE + b), ph ^ 1);
+                tc_fence_after();
+                tmem_st16(lane_base + A3_COL + b * A3_STR, r);
+                tmem_wait_st();
+                tc_fence_before();
+                warp_arrive(BAR(A3_FULL + b), lane);
+            }
+        }
+    } else if (warp >= W_E3 && warp < W_E3 + 4) {
+        /* ===================== conv III gather: dy in registers, dx across lanes, bias, clamp, store ========= */
+        const int t = (warp - W_E3) * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t it = 0, em = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const Unit un = unit_of(p, u);
+            const int c0 = un.band * kBandCols - 2, c = c0 + t;
+            float acc[5][5];                /* slot (n + j) % 5 holds output row q-2+j; [dx] */
+            #pragma unroll
+            for (int j = 0; j < 5; j++)
+                #pragma unroll
+                for (int d = 0; d < 5; d++) acc[j][d] = 0.f;
+            for (int n0 = 0; n0 < un.nrows; n0 += 5) {
+                #pragma unroll
+                for (int uu = 0; uu < 5; uu++) {
+                    const int n = n0 + uu;
+                    if (n < un.nrows) {
+                        const int q = un.ra - 2 + n;
+                        const uint32_t b = it & 1, ph = (it >> 1) & 1;
+                        uint32_t z[32];
+                        mbar_wait(BAR(M3_DONE + b), ph);
+                        tc_fence_after();
+                        tmem_ld32(lane_base + D3_COL + b * D3_STR, z);
+                        tmem_wait_ld();
+                        tc_fence_before();
+                        warp_arrive(BAR(D3_EMPTY + b), lane);
+                        if (q > 0 && q < p.dh - 1) {
+                            /* Z row q feeds output row q-2+j with dy = 2-j */
+                            #pragma unroll
+                            for (int j = 0; j < 5; j++)
+                                #pragma unroll
+                                for (int d = 0; d < 5; d++) acc[(uu + j) % 5][d] += __uint_as_float(z[(4 - j) * 5 + d]);
+                        } else if (q >= 0 && q < p.dh) {
+                            /* first / last image row also stands in for the clamped rows above / below it */
+                            #pragma unroll
+                            for (int j = 0; j < 5; j++)
+                                #pragma unroll
+                                for (int dyi = 0; dyi < 5; dyi++) {
+                                    const bool on = (dyi == 4 - j) || (q == 0 && dyi < 4 - j) || (q == p.dh - 1 && dyi > 4 - j);
+                                    if (on) {
+                                        #pragma unroll
+                                        for (int d = 0; d < 5; d++) acc[(uu + j) % 5][d] += __uint_as_float(z[dyi * 5 + d]);
+                                    }
+                                }
+                        }
+                        /* output row r = q-2 (slot uu) is complete */
+                        const int r = q - 2;
+                        if (r >= un.ra && r < un.rb) {
+                            float (*P)[128] = sP[em & 1]; em++;     /* consecutive emissions alternate buffers */
+                            #pragma unroll
+                            for (int d = 0; d < 5; d++) P[d][t] = acc[uu][d];
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            if (t >= 2 && t < 126 && c < p.dw) {
+                                float o = cBias3;
+                                #pragma unroll
+                                for (int d = 0; d < 5; d++) {
+                                    int cc = c + d - 2;
+                                    cc = cc < 0 ? 0 : (cc > p.dw - 1 ? p.dw - 1 : cc);
+                                    o += P[d][cc - c0];
+                                }
+                                o = fminf(fmaxf(o, 0.f), 255.f);
+                                p.out[(size_t)(r - p.row0) * p.dw + c] = o;
+                            }
+                        }
+                        #pragma unroll
+                        for (int d = 0; d < 5; d++) acc[uu][d] = 0.f;
+                        it++;
+                    }
+                }
+            }
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+    if (warp == W_ALLOC) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
 /* element (n, k) of an N x K K-major no-swizzle operand image: 8x8 core matrices of 128 B, K-adjacent ones contiguous */
 inline size_t canon_off(int n, int k, int K) { return (size_t)(n / 8) * ((K / 8) * 128) + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2; }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 } // namespace
 
 struct ConvTcState {
     unsigned char* d_wimg = nullptr;
+    EncodeTiledFn encode = nullptr;
     std::string err;
 };
 
@@ -366,6 +521,12 @@ int conv_tc_create(ConvTcState** out)
     if (e == cudaSuccess) e = cudaMemcpy(st->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(cBias2, SRCNN_B2, sizeof(SRCNN_B2));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(cBias3, &SRCNN_B3, sizeof(float));
+    if (e == cudaSuccess) {
+        void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+        e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e == cudaSuccess && (q != cudaDriverEntryPointSuccess || !fn)) e = cudaErrorNotSupported;
+        st->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
     if (e != cudaSuccess) { if (st->d_wimg) cudaFree(st->d_wimg); delete st; *out = nullptr; return (int)e; }
     *out = st;
     return 0;
@@ -384,18 +545,36 @@ int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, u
                    float* out, unsigned row0, unsigned row1, int num_sms, cudaStream_t s)
 {
     TcParams p;
-    p.y16 = y16; p.plane_halves = (size_t)g.pitch * g.rows; p.pitch = g.pitch; p.y16_rows = g.rows;
+    p.pitch = g.pitch; p.y16_rows = g.rows;
     p.dw = (int)dw; p.dh = (int)dh; p.out = out; p.row0 = (int)row0; p.row1 = (int)row1;
     p.bands = g.bands;
-    const int rows = (int)(row1 - row0), slots = 2 * num_sms;
-    /* row segments: about three units per resident CTA slot, never more units than a whole number of waves needs */
-    int nsegs = (3 * slots) / p.bands; if (nsegs < 1) nsegs = 1;
-    int seg_rows = (rows + nsegs - 1) / nsegs; if (seg_rows < 16) seg_rows = rows < 16 ? rows : 16;
-    p.seg_rows = seg_rows; p.nsegs = (rows + seg_rows - 1) / seg_rows;
+    const int rows = (int)(row1 - row0);
+    /* row segments: pick the count that minimises (waves x rows per unit incl. 4 halo rows + ~8 rows of refill) */
+    int best_nsegs = 1; long best_cost = -1;
+    for (int ns = 1; ns <= 256 && ns <= rows; ns++) {
+        const int sr = (rows + ns - 1) / ns;
+        const int nsegs = (rows + sr - 1) / sr;
+        const long waves = ((long)p.bands * nsegs + num_sms - 1) / num_sms;
+        const long cost = waves * (sr + 12);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nsegs = nsegs; }
+    }
+    p.seg_rows = (rows + best_nsegs - 1) / best_nsegs;
+    p.nsegs = (rows + p.seg_rows - 1) / p.seg_rows;
     p.wimg = st->d_wimg;
+
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = { (cuuint64_t)g.pitch, (cuuint64_t)g.rows };
+    const cuuint64_t gstr[1] = { (cuuint64_t)g.pitch * 2 };
+    const cuuint32_t box[2] = { BOX_W, CH_ROWS };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult cr = st->encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(y16), gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { st->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"; return 1; }
+
     const int units = p.bands * p.nsegs;
-    const int grid = units < slots ? units : slots;
-    conv_tc_kernel<<<grid, 128, 0, s>>>(p);
+    const int grid = units < num_sms ? units : num_sms;
+    conv_tc_kernel<<<grid, NWARPS * 32, 0, s>>>(p, map);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { st->err = cudaGetErrorString(e); return 1; }
     return 0;

@@ -111,8 +111,7 @@ Y16Geom y16_geometry(unsigned dw, unsigned strip_rows)
     return g;
 }
 
-/* thread = 8 consecutive halves (one 16 B store) of the padded FP16 plane E, and the same 8 positions of plane O
- * (O[x] = E[x+1]: lets odd lanes of the conv kernel read their window with aligned 32-bit loads) */
+/* thread = 8 consecutive halves (one 16 B store) of the replicate-padded FP16 plane */
 __global__ void __launch_bounds__(256)
 pack_y16_kernel(const float* __restrict__ y, int dw, int dh, int win_row0, __half* __restrict__ y16,
                 int pitch, int rows, int strip_row0)
@@ -123,26 +122,18 @@ pack_y16_kernel(const float* __restrict__ y, int dw, int dh, int win_row0, __hal
     int g = strip_row0 - kHaloRows + r;                   /* global row, replicate-clamped */
     g = g < 0 ? 0 : (g > dh - 1 ? dh - 1 : g);
     const float* src = y + (size_t)(g - win_row0) * dw;
-    float f[9];
-    #pragma unroll
-    for (int k = 0; k < 9; k++) {
-        int c = xo + k - kY16PadL;
-        c = c < 0 ? 0 : (c > dw - 1 ? dw - 1 : c);
-        f[k] = __ldg(src + c);
-    }
-    __half2 e[4], o[4];
+    __half2 h[4];
     #pragma unroll
     for (int k = 0; k < 4; k++) {
-        e[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
-        o[k] = __floats2half2_rn(f[2 * k + 1], f[2 * k + 2]);
+        int c0 = xo + 2 * k - kY16PadL, c1 = c0 + 1;
+        c0 = c0 < 0 ? 0 : (c0 > dw - 1 ? dw - 1 : c0);
+        c1 = c1 < 0 ? 0 : (c1 > dw - 1 ? dw - 1 : c1);
+        h[k] = __floats2half2_rn(__ldg(src + c0), __ldg(src + c1));
     }
-    uint4 v, w;
-    v.x = *reinterpret_cast<uint32_t*>(&e[0]); v.y = *reinterpret_cast<uint32_t*>(&e[1]);
-    v.z = *reinterpret_cast<uint32_t*>(&e[2]); v.w = *reinterpret_cast<uint32_t*>(&e[3]);
-    w.x = *reinterpret_cast<uint32_t*>(&o[0]); w.y = *reinterpret_cast<uint32_t*>(&o[1]);
-    w.z = *reinterpret_cast<uint32_t*>(&o[2]); w.w = *reinterpret_cast<uint32_t*>(&o[3]);
+    uint4 v;
+    v.x = *reinterpret_cast<uint32_t*>(&h[0]); v.y = *reinterpret_cast<uint32_t*>(&h[1]);
+    v.z = *reinterpret_cast<uint32_t*>(&h[2]); v.w = *reinterpret_cast<uint32_t*>(&h[3]);
     *reinterpret_cast<uint4*>(y16 + (size_t)r * pitch + xo) = v;
-    *reinterpret_cast<uint4*>(y16 + (size_t)rows * pitch + (size_t)r * pitch + xo) = w;
 }
 
 void launch_pack_y16(const float* y, unsigned dw, unsigned dh, unsigned win_row0, __half* y16, Y16Geom g,

@@ -227,7 +227,7 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, bool src_i
     /* 4./5. fused conv I+II+III on the Y plane */
     if (ctx->conv_mode == SRCNN_B200_CONV_TENSOR) {
         const Y16Geom g = y16_geometry(p.ow, orows);
-        CK(ctx->y16.ensure((size_t)2 * g.pitch * g.rows * sizeof(__half)));   /* planes E and O */
+        CK(ctx->y16.ensure((size_t)g.pitch * g.rows * sizeof(__half)));
         launch_pack_y16(P_dst, p.ow, p.oh, p.e0, static_cast<__half*>(ctx->y16.p), g, p.r0, s); ctx->launches++;
         st.mark();
         if (launch_conv_tc(ctx->tc, static_cast<const __half*>(ctx->y16.p), g, p.ow, p.oh, Yp, p.r0, p.r1,
@@ -642,7 +642,7 @@ int srcnn_b200_stage_conv(srcnn_b200_ctx* ctx, const float* y, unsigned w, unsig
         launch_conv_exact(Y, w, h, 0, h, O, 0, h, s); ctx->launches++;
     } else if (mode == SRCNN_B200_CONV_TENSOR) {
         const Y16Geom g = y16_geometry(w, h);
-        CK(ctx->y16.ensure((size_t)2 * g.pitch * g.rows * sizeof(__half)));   /* planes E and O */
+        CK(ctx->y16.ensure((size_t)g.pitch * g.rows * sizeof(__half)));
         launch_pack_y16(Y, w, h, 0, static_cast<__half*>(ctx->y16.p), g, 0, s); ctx->launches++;
         if (launch_conv_tc(ctx->tc, static_cast<const __half*>(ctx->y16.p), g, w, h, O, 0, h, ctx->num_sms, s)) {
             ctx->err = std::string("conv_tc: ") + conv_tc_error(ctx->tc);
