@@ -37,27 +37,28 @@
 #include <string>
 #include <vector>
 #include <cstring>
+#include <type_traits>
 
 namespace srcnn {
 
 namespace {
 
 constexpr int K1 = 96, N1 = 64;     /* conv I   GEMM */
-constexpr int K2 = 64, N2 = 32;     /* conv II  GEMM */
+constexpr int K2 = 64, N2 = 32;     /* conv II  GEMM (+ one K=16 step against a constant-1 operand that adds the bias) */
 constexpr int K3 = 32, N3 = 32;     /* conv III GEMM (taps as N) */
-constexpr int B1_BYTES = N1 * K1 * 2, B2_BYTES = N2 * K2 * 2, B3_BYTES = N3 * K3 * 2;
-constexpr int WIMG_BYTES = B1_BYTES + B2_BYTES + B3_BYTES;
+constexpr int B1_BYTES = N1 * K1 * 2, B2_BYTES = N2 * K2 * 2, B3_BYTES = N3 * K3 * 2, B2B_BYTES = N2 * 16 * 2;
+constexpr int WIMG_BYTES = B1_BYTES + B2_BYTES + B3_BYTES + B2B_BYTES;
 
 /* TMEM columns (512 allocated); every region double-buffered: index b = row & 1 */
-constexpr uint32_t D1_COL = 0, D2_COL = 128, D3_COL = 192, A1_COL = 256, A2_COL = 352, A3_COL = 416;
+constexpr uint32_t D1_COL = 0, D2_COL = 128, D3_COL = 192, A1_COL = 256, A2_COL = 352, A3_COL = 416, AC_COL = 448;
 constexpr uint32_t D1_STR = 64, D2_STR = 32, D3_STR = 32, A1_STR = 48, A2_STR = 32, A3_STR = 16;
 
 /* Y16 staging ring */
 constexpr int CH_ROWS = 8, BOX_W = 144, NST = 4;
 constexpr int CH_BYTES = CH_ROWS * BOX_W * 2;
 
-/* warp roles */
-constexpr int W_TMA = 0, W_MMA1 = 1, W_ALLOC = 2, W_MMA23 = 3, W_IM2COL = 4, W_E1 = 8, W_E2 = 12, W_E3 = 16, NWARPS = 20;
+/* warp roles: one control warpgroup + four 4-warp groups (TMEM lane quarter = warp & 3) */
+constexpr int W_TMA = 0, W_MMA1 = 1, W_MMA2 = 2, W_MMA3 = 3, W_IM2COL = 4, W_E1 = 8, W_E2 = 12, W_E3 = 16, NWARPS = 20;
 
 /* barrier indices.  M?_DONE[b] fires when the MMAs of layer ? for a row with parity b have completed: it both frees the
  * A operand region for the producer group and publishes the accumulator to the consumer group. */
@@ -65,7 +66,6 @@ enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + 2, D1_E
        A2_FULL = D1_EMPTY + 2, M2_DONE = A2_FULL + 2, D2_EMPTY = M2_DONE + 2,
        A3_FULL = D2_EMPTY + 2, M3_DONE = A3_FULL + 2, D3_EMPTY = M3_DONE + 2, NBAR = D3_EMPTY + 2 };
 
-__constant__ float cBias2[32];
 __constant__ float cBias3;
 
 /* ---------------------------------------------------------------- PTX helpers */
@@ -118,7 +118,14 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st()    { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld()    { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* r)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -136,10 +143,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* r)
                  : "r"(addr) : "memory");
 }
 /* two FP32 -> packed FP16x2 with ReLU in one instruction; `lo` lands in the low half (even K index) */
-__device__ __forceinline__ uint32_t cvt_relu_h2(float lo, float hi)
+__device__ __forceinline__ uint32_t cvt_relu_h2(uint32_t lo, uint32_t hi)
 {
     uint32_t d;
-    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
     return d;
 }
 /* warp-uniform code, one elected lane issues (keeps descriptors / addresses in uniform registers) */
@@ -163,7 +170,7 @@ struct TcParams {
     float* out;                 /* rows [row0,row1) x dw */
     int row0, row1;
     int bands, seg_rows, nsegs;
-    const unsigned char* wimg;  /* B1 | B2 | B3 operand images */
+    const unsigned char* wimg;  /* B1 | B2 | B3 | B2-bias operand images */
 };
 
 struct Unit { int band, ra, rb, nrows; };
@@ -176,6 +183,12 @@ __device__ __forceinline__ Unit unit_of(const TcParams& p, int u)
     x.rb = min(x.ra + p.seg_rows, p.row1);
     x.nrows = x.rb - x.ra + 4;              /* intermediate rows q = ra-2 .. rb+1 */
     return x;
+}
+__device__ __forceinline__ int total_rows(const TcParams& p, int units)
+{
+    int total = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) total += unit_of(p, u).nrows;
+    return total;
 }
 
 __global__ void __launch_bounds__(NWARPS * 32, 1)
@@ -204,7 +217,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == W_ALLOC) {
+    if (warp == W_MMA2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -214,96 +227,131 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     tc_fence_after();
 
     const uint32_t tmem = s_tmem;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);     /* this warp's TMEM lane quarter */
+    if (warp >= W_E2 && warp < W_E2 + 4) {
+        /* constant A operand of the bias K-step of conv II: k = 0, 1 -> 1.0, k = 2..15 -> 0 */
+        uint32_t r[8] = { 0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u };
+        tmem_st8(lane_base + AC_COL, r);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
     const uint32_t bar0 = smem_u32(&s_bar[0]);
     auto BAR = [&](int i) -> uint32_t { return bar0 + 8u * (uint32_t)i; };
     const int units = p.bands * p.nsegs;
 
-    if (warp == W_TMA) {
-        /* ===================== TMA producer: Y16 rows of the current unit, 8-row chunks ===================== */
-        uint32_t ck = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const Unit un = unit_of(p, u);
-            const int x0 = (un.band * kBandCols + 2) & ~7;            /* 16 B aligned box origin */
-            const int yr0 = un.ra - p.row0;                           /* plane row of image row ra-6 */
-            const int nch = (un.nrows + 8 + CH_ROWS - 1) / CH_ROWS;
-            for (int j = 0; j < nch; j++, ck++) {
-                const uint32_t s = ck % NST, k = ck / NST;
-                mbar_wait(BAR(Y_EMPTY + s), (k & 1) ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(BAR(Y_FULL + s), CH_BYTES);
-                    tma_load_2d(smem_u32(sY) + s * CH_BYTES, &ymap, x0, yr0 + j * CH_ROWS, BAR(Y_FULL + s));
+    if (warp < 4) {
+        /* ============================ control warpgroup: TMA producer + three MMA issuers ==================== */
+        reg_dec<48>();
+        if (warp == W_TMA) {
+            /* Y16 rows of the current unit, 8-row chunks into a 4-stage ring */
+            uint32_t ck = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const Unit un = unit_of(p, u);
+                const int x0 = (un.band * kBandCols + 2) & ~7;            /* 16 B aligned box origin */
+                const int yr0 = un.ra - p.row0;                           /* plane row of image row ra-6 */
+                const int nch = (un.nrows + 8 + CH_ROWS - 1) / CH_ROWS;
+                for (int j = 0; j < nch; j++, ck++) {
+                    const uint32_t s = ck % NST, k = ck / NST;
+                    mbar_wait(BAR(Y_EMPTY + s), (k & 1) ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(BAR(Y_FULL + s), CH_BYTES);
+                        tma_load_2d(smem_u32(sY) + s * CH_BYTES, &ymap, x0, yr0 + j * CH_ROWS, BAR(Y_FULL + s));
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
+            }
+        } else {
+            /* MMA issuers: warp-uniform control flow, one elected lane issues; the rows of all units form one
+             * continuous stream, the loop is unrolled by two so that buffer index b is a compile-time constant */
+            const int total = total_rows(p, units);
+            if (warp == W_MMA1) {
+                const uint64_t db = umma_desc(smem_u32(sW), 128, (K1 / 8) * 128);
+                auto step = [&](auto B, uint32_t ph) {
+                    constexpr uint32_t b = decltype(B)::value;
+                    mbar_wait(BAR(A1_FULL + b), ph);
+                    mbar_wait(BAR(D1_EMPTY + b), ph ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        #pragma unroll
+                        for (int s = 0; s < K1 / 16; s++)
+                            umma_ts(tmem + D1_COL + b * D1_STR, tmem + A1_COL + b * A1_STR + 8 * s, db + 16 * s, umma_idesc(N1), s > 0);
+                        umma_commit(BAR(M1_DONE + b));
+                    }
+                    __syncwarp();
+                };
+                #pragma unroll 1
+                #pragma unroll 1
+        for (int g = 0; g < total; g += 2) {
+                    const uint32_t ph = (g >> 1) & 1;
+                    step(std::integral_constant<uint32_t, 0>{}, ph);
+                    if (g + 1 < total) step(std::integral_constant<uint32_t, 1>{}, ph);
+                }
+            } else if (warp == W_MMA2) {
+                const uint64_t db = umma_desc(smem_u32(sW) + B1_BYTES, 128, (K2 / 8) * 128);
+                const uint64_t dbb = umma_desc(smem_u32(sW) + B1_BYTES + B2_BYTES + B3_BYTES, 128, 256);
+                auto step = [&](auto B, uint32_t ph) {
+                    constexpr uint32_t b = decltype(B)::value;
+                    mbar_wait(BAR(A2_FULL + b), ph);
+                    mbar_wait(BAR(D2_EMPTY + b), ph ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        #pragma unroll
+                        for (int s = 0; s < K2 / 16; s++)
+                            umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR + 8 * s, db + 16 * s, umma_idesc(N2), s > 0);
+                        umma_ts(tmem + D2_COL + b * D2_STR, tmem + AC_COL, dbb, umma_idesc(N2), 1);     /* + bias */
+                        umma_commit(BAR(M2_DONE + b));
+                    }
+                    __syncwarp();
+                };
+                #pragma unroll 1
+                #pragma unroll 1
+        for (int g = 0; g < total; g += 2) {
+                    const uint32_t ph = (g >> 1) & 1;
+                    step(std::integral_constant<uint32_t, 0>{}, ph);
+                    if (g + 1 < total) step(std::integral_constant<uint32_t, 1>{}, ph);
+                }
+            } else {
+                const uint64_t db = umma_desc(smem_u32(sW) + B1_BYTES + B2_BYTES, 128, (K3 / 8) * 128);
+                auto step = [&](auto B, uint32_t ph) {
+                    constexpr uint32_t b = decltype(B)::value;
+                    mbar_wait(BAR(A3_FULL + b), ph);
+                    mbar_wait(BAR(D3_EMPTY + b), ph ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        #pragma unroll
+                        for (int s = 0; s < K3 / 16; s++)
+                            umma_ts(tmem + D3_COL + b * D3_STR, tmem + A3_COL + b * A3_STR + 8 * s, db + 16 * s, umma_idesc(N3), s > 0);
+                        umma_commit(BAR(M3_DONE + b));
+                    }
+                    __syncwarp();
+                };
+                #pragma unroll 1
+                #pragma unroll 1
+        for (int g = 0; g < total; g += 2) {
+                    const uint32_t ph = (g >> 1) & 1;
+                    step(std::integral_constant<uint32_t, 0>{}, ph);
+                    if (g + 1 < total) step(std::integral_constant<uint32_t, 1>{}, ph);
+                }
             }
         }
-    } else if (warp == W_MMA1) {
-        /* ===================== MMA issuer, conv I.  Rows of all units form one continuous stream. ============
-         * Warp-uniform control flow; one elected lane issues. */
-        int total = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) total += unit_of(p, u).nrows;
-        const uint64_t db1 = umma_desc(smem_u32(sW), 128, (K1 / 8) * 128);
-        for (int g = 0; g < total; g++) {
-            const uint32_t b = g & 1, ph = (g >> 1) & 1;
-            mbar_wait(BAR(A1_FULL + b), ph);
-            mbar_wait(BAR(D1_EMPTY + b), ph ^ 1);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t d = tmem + D1_COL + b * D1_STR, a = tmem + A1_COL + b * A1_STR;
-                #pragma unroll
-                for (int s = 0; s < K1 / 16; s++) umma_ts(d, a + 8 * s, db1 + 16 * s, umma_idesc(N1), s > 0);
-                umma_commit(BAR(M1_DONE + b));
-            }
-            __syncwarp();
-        }
-    } else if (warp == W_MMA23) {
-        /* ===================== MMA issuer, conv II (row g) and conv III (row g-1) =========================== */
-        int total = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) total += unit_of(p, u).nrows;
-        const uint64_t db2 = umma_desc(smem_u32(sW) + B1_BYTES, 128, (K2 / 8) * 128);
-        const uint64_t db3 = umma_desc(smem_u32(sW) + B1_BYTES + B2_BYTES, 128, (K3 / 8) * 128);
-        for (int g = 0; g < total + 1; g++) {
-            if (g < total) {
-                const uint32_t b = g & 1, ph = (g >> 1) & 1;
-                mbar_wait(BAR(A2_FULL + b), ph);
-                mbar_wait(BAR(D2_EMPTY + b), ph ^ 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t d = tmem + D2_COL + b * D2_STR, a = tmem + A2_COL + b * A2_STR;
-                    #pragma unroll
-                    for (int s = 0; s < K2 / 16; s++) umma_ts(d, a + 8 * s, db2 + 16 * s, umma_idesc(N2), s > 0);
-                    umma_commit(BAR(M2_DONE + b));
-                }
-                __syncwarp();
-            }
-            if (g >= 1) {
-                const int m = g - 1; const uint32_t b = m & 1, ph = (m >> 1) & 1;
-                mbar_wait(BAR(A3_FULL + b), ph);
-                mbar_wait(BAR(D3_EMPTY + b), ph ^ 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t d = tmem + D3_COL + b * D3_STR, a = tmem + A3_COL + b * A3_STR;
-                    #pragma unroll
-                    for (int s = 0; s < K3 / 16; s++) umma_ts(d, a + 8 * s, db3 + 16 * s, umma_idesc(N3), s > 0);
-                    umma_commit(BAR(M3_DONE + b));
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp >= W_IM2COL && warp < W_IM2COL + 4) {
+    } else if (warp < W_E1) {
         /* ===================== im2col: smem Y16 ring -> rolling 9x10 register window -> A1 in TMEM ========== */
+        reg_inc<128>();
         const int t = (warp - W_IM2COL) * 32 + lane;
-        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t it = 0, ck = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const Unit un = unit_of(p, u);
             const int hw = ((un.band * kBandCols + 2) & 7) + t;       /* half offset of this lane's window in the box */
-            const uint32_t woff = (uint32_t)(hw >> 1) * 4u, sh = (uint32_t)(hw & 1) * 16u;
+            const uint32_t woff = smem_u32(sY) + (uint32_t)(hw >> 1) * 4u, sh = (uint32_t)(hw & 1) * 16u;
             const int last_rho = un.nrows + 7;
-            uint32_t W[9][5];
-            auto fetch = [&](int rho, uint32_t* w5) {
+            uint32_t W[9][5];                                         /* rows q-4 .. q+4, two halves per word */
+            auto fetch = [&](int rho, uint32_t (&w5)[5]) {
                 const uint32_t c = ck + (uint32_t)(rho / CH_ROWS), s = c % NST;
                 if ((rho % CH_ROWS) == 0) mbar_wait(BAR(Y_FULL + s), (c / NST) & 1);
-                const uint32_t a = smem_u32(sY) + s * CH_BYTES + (uint32_t)(rho % CH_ROWS) * (BOX_W * 2) + woff;
+                const uint32_t a = woff + s * CH_BYTES + (uint32_t)(rho % CH_ROWS) * (BOX_W * 2);
                 uint32_t x[6];
                 #pragma unroll
                 for (int j = 0; j < 6; j++) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[j]) : "r"(a + 4u * j));
@@ -313,170 +361,169 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             };
             #pragma unroll
             for (int i = 0; i < 8; i++) fetch(i, W[i]);
-            for (int n0 = 0; n0 < un.nrows; n0 += 9) {
+            #pragma unroll 1
+            for (int n = 0; n < un.nrows; n++, it++) {
+                fetch(n + 8, W[8]);
+                const uint32_t b = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(BAR(M1_DONE) + 8u * b, ph ^ 1);            /* MMA1 of row it-2 has consumed A1[b] */
+                tc_fence_after();
+                const uint32_t dst = lane_base + A1_COL + b * A1_STR;
+                uint32_t r[16];
                 #pragma unroll
-                for (int uu = 0; uu < 9; uu++) {
-                    const int n = n0 + uu;
-                    if (n < un.nrows) {
-                        fetch(n + 8, W[(uu + 8) % 9]);
-                        const uint32_t b = it & 1, ph = (it >> 1) & 1;
-                        mbar_wait(BAR(M1_DONE + b), ph ^ 1);
-                        tc_fence_after();
-                        const uint32_t dst = lane_base + A1_COL + b * A1_STR;
-                        uint32_t r[16];
-                        #pragma unroll
-                        for (int m = 0; m < 16; m++) r[m] = W[(uu + m / 5) % 9][m % 5];
-                        tmem_st16(dst, r);
-                        #pragma unroll
-                        for (int m = 0; m < 16; m++) r[m] = W[(uu + (m + 16) / 5) % 9][(m + 16) % 5];
-                        tmem_st16(dst + 16, r);
-                        #pragma unroll
-                        for (int m = 0; m < 13; m++) r[m] = W[(uu + (m + 32) / 5) % 9][(m + 32) % 5];
-                        r[13] = 0x3C003C00u;                  /* k = 90, 91: constant 1.0 (bias inputs) */
-                        r[14] = 0u; r[15] = 0u;
-                        tmem_st16(dst + 32, r);
-                        tmem_wait_st();
-                        tc_fence_before();
-                        warp_arrive(BAR(A1_FULL + b), lane);
-                        it++;
-                    }
-                }
+                for (int m = 0; m < 16; m++) r[m] = W[m / 5][m % 5];
+                tmem_st16(dst, r);
+                #pragma unroll
+                for (int m = 0; m < 16; m++) r[m] = W[(m + 16) / 5][(m + 16) % 5];
+                tmem_st16(dst + 16, r);
+                #pragma unroll
+                for (int m = 0; m < 13; m++) r[m] = W[(m + 32) / 5][(m + 32) % 5];
+                r[13] = 0x3C003C00u;                          /* k = 90, 91: constant 1.0 (bias inputs) */
+                r[14] = 0u; r[15] = 0u;
+                tmem_st16(dst + 32, r);
+                tmem_wait_st();
+                tc_fence_before();
+                warp_arrive(BAR(A1_FULL) + 8u * b, lane);
+                #pragma unroll
+                for (int i = 0; i < 8; i++)                   /* roll the window down one row */
+                    #pragma unroll
+                    for (int j = 0; j < 5; j++) W[i][j] = W[i + 1][j];
             }
             ck += (uint32_t)((un.nrows + 8 + CH_ROWS - 1) / CH_ROWS);
         }
-    } else if (warp >= W_E1 && warp < W_E1 + 4) {
+    } else if (warp < W_E2) {
         /* ===================== epilogue I: D1 -> ReLU -> FP16 -> A2 (bias is already inside the GEMM) ======== */
-        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t it = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int nrows = unit_of(p, u).nrows;
-            for (int n = 0; n < nrows; n++, it++) {
-                const uint32_t b = it & 1, ph = (it >> 1) & 1;
-                uint32_t v[32], r0[16], r1[16];
-                mbar_wait(BAR(M1_DONE + b), ph);
-                tc_fence_after();
-                tmem_ld32(lane_base + D1_COL + b * D1_STR, v);
-                tmem_wait_ld();
-                #pragma unroll
-                for (int m = 0; m < 16; m++) r0[m] = cvt_relu_h2(__uint_as_float(v[2 * m]), __uint_as_float(v[2 * m + 1]));
-                tmem_ld32(lane_base + D1_COL + b * D1_STR + 32, v);
-                tmem_wait_ld();
-                tc_fence_before();
-                warp_arrive(BAR(D1_EMPTY + b), lane);
-                #pragma unroll
-                for (int m = 0; m < 16; m++) r1[m] = cvt_relu_h2(__uint_as_float(v[2 * m]), __uint_as_float(v[2 * m + 1]));
-                mbar_wait(BAR(M2_DONE + b), ph ^ 1);
-                tc_fence_after();
-                tmem_st16(lane_base + A2_COL + b * A2_STR, r0);
-                tmem_st16(lane_base + A2_COL + b * A2_STR + 16, r1);
-                tmem_wait_st();
-                tc_fence_before();
-                warp_arrive(BAR(A2_FULL + b), lane);
-            }
+        const int total = total_rows(p, units);
+        auto step = [&](auto B, uint32_t ph) {
+            constexpr uint32_t b = decltype(B)::value;
+            uint32_t v[64];
+            mbar_wait(BAR(M1_DONE + b), ph);
+            tc_fence_after();
+            tmem_ld32(lane_base + D1_COL + b * D1_STR, v);
+            tmem_ld32(lane_base + D1_COL + b * D1_STR + 32, v + 32);
+            tmem_wait_ld();
+            tc_fence_before();
+            warp_arrive(BAR(D1_EMPTY + b), lane);
+            #pragma unroll
+            for (int m = 0; m < 32; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
+            mbar_wait(BAR(M2_DONE + b), ph ^ 1);                      /* MMA2 of row it-2 has consumed A2[b] */
+            tc_fence_after();
+            tmem_st16(lane_base + A2_COL + b * A2_STR, v);
+            tmem_st16(lane_base + A2_COL + b * A2_STR + 16, v + 16);
+            tmem_wait_st();
+            tc_fence_before();
+            warp_arrive(BAR(A2_FULL + b), lane);
+        };
+        #pragma unroll 1
+        for (int g = 0; g < total; g += 2) {
+            const uint32_t ph = (g >> 1) & 1;
+            step(std::integral_constant<uint32_t, 0>{}, ph);
+            if (g + 1 < total) step(std::integral_constant<uint32_t, 1>{}, ph);
         }
-    } else if (warp >= W_E2 && warp < W_E2 + 4) {
-        /* ===================== epilogue II: D2 + bias -> ReLU -> FP16 -> A3 ================================= */
-        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t it = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int nrows = unit_of(p, u).nrows;
-            for (int n = 0; n < nrows; n++, it++) {
-                const uint32_t b = it & 1, ph = (it >> 1) & 1;
-                uint32_t v[32], r[16];
-                mbar_wait(BAR(M2_DONE + b), ph);
-                tc_fence_after();
-                tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
-                tmem_wait_ld();
-                tc_fence_before();
-                warp_arrive(BAR(D2_EMPTY + b), lane);
-                #pragma unroll
-                for (int m = 0; m < 16; m++)
-                    r[m] = cvt_relu_h2(__uint_as_float(v[2 * m]) + cBias2[2 * m], __uint_as_float(v[2 * m + 1]) + cBias2[2 * m + 1]);
-                mbar_wait(BAR(M3_DONE + b), ph ^ 1);
-                tc_fence_after();
-                tmem_st16(lane_base + A3_COL + b * A3_STR, r);
-                tmem_wait_st();
-                tc_fence_before();
-                warp_arrive(BAR(A3_FULL + b), lane);
-            }
+    } else if (warp < W_E3) {
+        /* ===================== epilogue II: D2 (bias included) -> ReLU -> FP16 -> A3 ========================= */
+        const int total = total_rows(p, units);
+        auto step = [&](auto B, uint32_t ph) {
+            constexpr uint32_t b = decltype(B)::value;
+            uint32_t v[32];
+            mbar_wait(BAR(M2_DONE + b), ph);
+            tc_fence_after();
+            tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
+            tmem_wait_ld();
+            tc_fence_before();
+            warp_arrive(BAR(D2_EMPTY + b), lane);
+            #pragma unroll
+            for (int m = 0; m < 16; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
+            mbar_wait(BAR(M3_DONE + b), ph ^ 1);
+            tc_fence_after();
+            tmem_st16(lane_base + A3_COL + b * A3_STR, v);
+            tmem_wait_st();
+            tc_fence_before();
+            warp_arrive(BAR(A3_FULL + b), lane);
+        };
+        #pragma unroll 1
+        for (int g = 0; g < total; g += 2) {
+            const uint32_t ph = (g >> 1) & 1;
+            step(std::integral_constant<uint32_t, 0>{}, ph);
+            if (g + 1 < total) step(std::integral_constant<uint32_t, 1>{}, ph);
         }
-    } else if (warp >= W_E3 && warp < W_E3 + 4) {
+    } else {
         /* ===================== conv III gather: dy in registers, dx across lanes, bias, clamp, store ========= */
+        reg_inc<112>();
         const int t = (warp - W_E3) * 32 + lane;
-        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t it = 0, em = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const Unit un = unit_of(p, u);
             const int c0 = un.band * kBandCols - 2, c = c0 + t;
-            float acc[5][5];                /* slot (n + j) % 5 holds output row q-2+j; [dx] */
+            const bool writer = (t >= 2 && t < 126 && c < p.dw);
+            int pidx[5];                        /* lane of column clamp(c + dx) -- conv III clamps its input plane */
+            #pragma unroll
+            for (int d = 0; d < 5; d++) {
+                int cc = c + d - 2;
+                cc = cc < 0 ? 0 : (cc > p.dw - 1 ? p.dw - 1 : cc);
+                cc -= c0;
+                pidx[d] = d * 128 + (cc < 0 ? 0 : (cc > 127 ? 127 : cc));
+            }
+            float acc[5][5];                    /* acc[j][dx]: partial of output row q-2+j */
             #pragma unroll
             for (int j = 0; j < 5; j++)
                 #pragma unroll
                 for (int d = 0; d < 5; d++) acc[j][d] = 0.f;
-            for (int n0 = 0; n0 < un.nrows; n0 += 5) {
-                #pragma unroll
-                for (int uu = 0; uu < 5; uu++) {
-                    const int n = n0 + uu;
-                    if (n < un.nrows) {
-                        const int q = un.ra - 2 + n;
-                        const uint32_t b = it & 1, ph = (it >> 1) & 1;
-                        uint32_t z[32];
-                        mbar_wait(BAR(M3_DONE + b), ph);
-                        tc_fence_after();
-                        tmem_ld32(lane_base + D3_COL + b * D3_STR, z);
-                        tmem_wait_ld();
-                        tc_fence_before();
-                        warp_arrive(BAR(D3_EMPTY + b), lane);
-                        if (q > 0 && q < p.dh - 1) {
-                            /* Z row q feeds output row q-2+j with dy = 2-j */
-                            #pragma unroll
-                            for (int j = 0; j < 5; j++)
-                                #pragma unroll
-                                for (int d = 0; d < 5; d++) acc[(uu + j) % 5][d] += __uint_as_float(z[(4 - j) * 5 + d]);
-                        } else if (q >= 0 && q < p.dh) {
-                            /* first / last image row also stands in for the clamped rows above / below it */
-                            #pragma unroll
-                            for (int j = 0; j < 5; j++)
-                                #pragma unroll
-                                for (int dyi = 0; dyi < 5; dyi++) {
-                                    const bool on = (dyi == 4 - j) || (q == 0 && dyi < 4 - j) || (q == p.dh - 1 && dyi > 4 - j);
-                                    if (on) {
-                                        #pragma unroll
-                                        for (int d = 0; d < 5; d++) acc[(uu + j) % 5][d] += __uint_as_float(z[dyi * 5 + d]);
-                                    }
-                                }
-                        }
-                        /* output row r = q-2 (slot uu) is complete */
-                        const int r = q - 2;
-                        if (r >= un.ra && r < un.rb) {
-                            float (*P)[128] = sP[em & 1]; em++;     /* consecutive emissions alternate buffers */
-                            #pragma unroll
-                            for (int d = 0; d < 5; d++) P[d][t] = acc[uu][d];
-                            asm volatile("bar.sync 1, 128;" ::: "memory");
-                            if (t >= 2 && t < 126 && c < p.dw) {
-                                float o = cBias3;
-                                #pragma unroll
-                                for (int d = 0; d < 5; d++) {
-                                    int cc = c + d - 2;
-                                    cc = cc < 0 ? 0 : (cc > p.dw - 1 ? p.dw - 1 : cc);
-                                    o += P[d][cc - c0];
-                                }
-                                o = fminf(fmaxf(o, 0.f), 255.f);
-                                p.out[(size_t)(r - p.row0) * p.dw + c] = o;
-                            }
-                        }
+            #pragma unroll 1
+            for (int n = 0; n < un.nrows; n++, it++) {
+                const int q = un.ra - 2 + n;
+                const uint32_t b = it & 1, ph = (it >> 1) & 1;
+                uint32_t z[32];
+                mbar_wait(BAR(M3_DONE) + 8u * b, ph);
+                tc_fence_after();
+                tmem_ld32(lane_base + D3_COL + b * D3_STR, z);
+                tmem_wait_ld();
+                tc_fence_before();
+                warp_arrive(BAR(D3_EMPTY) + 8u * b, lane);
+                if (q > 0 && q < p.dh - 1) {
+                    /* Z row q feeds output row q-2+j with dy = 2-j */
+                    #pragma unroll
+                    for (int j = 0; j < 5; j++)
                         #pragma unroll
-                        for (int d = 0; d < 5; d++) acc[uu][d] = 0.f;
-                        it++;
+                        for (int d = 0; d < 5; d++) acc[j][d] += __uint_as_float(z[(4 - j) * 5 + d]);
+                } else if (q >= 0 && q < p.dh) {
+                    /* first / last image row also stands in for the clamped rows above / below it */
+                    #pragma unroll
+                    for (int j = 0; j < 5; j++)
+                        #pragma unroll
+                        for (int dyi = 0; dyi < 5; dyi++) {
+                            const bool on = (dyi == 4 - j) || (q == 0 && dyi < 4 - j) || (q == p.dh - 1 && dyi > 4 - j);
+                            #pragma unroll
+                            for (int d = 0; d < 5; d++) acc[j][d] += on ? __uint_as_float(z[dyi * 5 + d]) : 0.f;
+                        }
+                }
+                /* output row r = q-2 (acc[0]) is complete */
+                const int r = q - 2;
+                if (r >= un.ra && r < un.rb) {
+                    float* P = &sP[em & 1][0][0]; em++;     /* consecutive emissions alternate buffers */
+                    #pragma unroll
+                    for (int d = 0; d < 5; d++) P[d * 128 + t] = acc[0][d];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (writer) {
+                        float o = cBias3;
+                        #pragma unroll
+                        for (int d = 0; d < 5; d++) o += P[pidx[d]];
+                        o = fminf(fmaxf(o, 0.f), 255.f);
+                        p.out[(size_t)(r - p.row0) * p.dw + c] = o;
                     }
                 }
+                #pragma unroll
+                for (int j = 0; j < 4; j++)
+                    #pragma unroll
+                    for (int d = 0; d < 5; d++) acc[j][d] = acc[j + 1][d];
+                #pragma unroll
+                for (int d = 0; d < 5; d++) acc[4][d] = 0.f;
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == W_ALLOC) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+    if (warp == W_MMA2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
 /* element (n, k) of an N x K K-major no-swizzle operand image: 8x8 core matrices of 128 B, K-adjacent ones contiguous */
@@ -517,9 +564,16 @@ int conv_tc_create(ConvTcState** out)
     for (int n = 0; n < 25; n++)
         for (int k = 0; k < K3; k++) put(B1_BYTES + B2_BYTES, n, k, K3, SRCNN_W3[n][k]);
 
+    /* conv II bias as a 32 x 16 operand for the constant-1 K-step: k = 0 hi part, k = 1 lo part */
+    for (int n = 0; n < N2; n++) {
+        const float b = SRCNN_B2[n];
+        const float hi = __half2float(__float2half_rn(b));
+        put(B1_BYTES + B2_BYTES + B3_BYTES, n, 0, 16, hi);
+        put(B1_BYTES + B2_BYTES + B3_BYTES, n, 1, 16, b - hi);
+    }
+
     cudaError_t e = cudaMalloc(&st->d_wimg, WIMG_BYTES);
     if (e == cudaSuccess) e = cudaMemcpy(st->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(cBias2, SRCNN_B2, sizeof(SRCNN_B2));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(cBias3, &SRCNN_B3, sizeof(float));
     if (e == cudaSuccess) {
         void* fn = nullptr; cudaDriverEntryPointQueryResult q;
