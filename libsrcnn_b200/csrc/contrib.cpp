@@ -91,6 +91,16 @@ void build_axis_table(int filter, unsigned dst, unsigned src, AxisTable& t)
         }
         t.left[u] = lo; t.right[u] = hi;
     }
+    t.dense = (int)src >= t.win;
+    if (t.dense) {
+        t.dleft.assign(dst, 0); t.dw.assign((size_t)dst * t.win, 0.0);
+        for (unsigned u = 0; u < dst; u++) {
+            int dl = t.left[u];
+            if (dl + t.win > (int)src) dl = (int)src - t.win;      /* shift the window left, zero weights in front */
+            t.dleft[u] = dl;
+            for (int i = t.left[u]; i <= t.right[u]; i++) t.dw[(size_t)u * t.win + (i - dl)] = t.w[(size_t)u * t.win + (i - t.left[u])];
+        }
+    }
 }
 
 } // namespace srcnn

@@ -12,6 +12,12 @@ struct AxisTable {
     int win = 0;                     /* weights per destination index (row pitch of w) */
     std::vector<int>    left, right; /* inclusive source range per destination index   */
     std::vector<double> w;           /* [dst][win], zero padded                        */
+    /* dense form (only when src >= win): every destination index reads exactly `win` in-bounds source samples
+     * starting at dleft; taps outside [left,right] carry weight 0 (leading/trailing zero terms leave the
+     * ascending-order double accumulation unchanged), so kernels need no per-sample tap count */
+    bool dense = false;
+    std::vector<int>    dleft;
+    std::vector<double> dw;
 };
 
 double filter_support(int filter);

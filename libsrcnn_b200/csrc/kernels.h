@@ -15,6 +15,9 @@ struct AxisTableDev {
     const int*    count;    /* [dst]  number of taps (right-left+1) */
     const double* w;        /* [dst][win]                           */
     int           win;
+    /* dense form (NULL if unavailable): exactly win in-bounds taps from dleft, zero weights where unused */
+    const int*    dleft;
+    const double* dw;
 };
 
 /* geometry of the FP16 conv-input plane consumed by the tensor-core kernel (see DESIGN.md "Y16 plane") */

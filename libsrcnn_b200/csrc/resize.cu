@@ -53,13 +53,69 @@ resize_vertical_kernel(const float* __restrict__ in, size_t in_plane_stride, uns
         *dst = __double2float_rn(acc[0]);
 }
 
+/* vertical, dense table with exactly W taps (every magnification): thread = 4 adjacent columns, VROWS destination rows
+ * are NOT shared (each destination row has its own taps); no tap count, no predicates */
+template <int W>
+__global__ void __launch_bounds__(128)
+resize_vertical_dense_kernel(const float* __restrict__ in, size_t in_plane_stride, unsigned width, unsigned in_row0,
+                             float* __restrict__ out, size_t out_plane_stride, unsigned out_row0, unsigned out_rows,
+                             const int* __restrict__ dleft, const double* __restrict__ dw)
+{
+    const unsigned x  = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const unsigned yy = blockIdx.y;
+    const unsigned pl = blockIdx.z;
+    if (x >= width) return;
+    const unsigned gy = out_row0 + yy;
+    const int left = __ldg(dleft + gy);
+    const double* w = dw + (size_t)gy * W;
+    const float* src = in + pl * in_plane_stride + (size_t)(left - (int)in_row0) * width + x;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    #pragma unroll
+    for (int i = 0; i < W; i++) {
+        const double wi = __ldg(w + i);
+        const float4 p = __ldg(reinterpret_cast<const float4*>(src + (size_t)i * width));
+        a0 = __dadd_rn(a0, __dmul_rn(wi, (double)p.x));
+        a1 = __dadd_rn(a1, __dmul_rn(wi, (double)p.y));
+        a2 = __dadd_rn(a2, __dmul_rn(wi, (double)p.z));
+        a3 = __dadd_rn(a3, __dmul_rn(wi, (double)p.w));
+    }
+    *reinterpret_cast<float4*>(out + pl * out_plane_stride + (size_t)yy * width + x) =
+        make_float4(__double2float_rn(a0), __double2float_rn(a1), __double2float_rn(a2), __double2float_rn(a3));
+}
+
+template <int W>
+static void launch_vdense(const float* in, size_t ips, unsigned width, unsigned in_row0, float* out, size_t ops,
+                          unsigned out_row0, unsigned out_rows, unsigned nplanes, const AxisTableDev& t, cudaStream_t s)
+{
+    dim3 grid((width / 4 + 127) / 128, out_rows, nplanes);
+    resize_vertical_dense_kernel<W><<<grid, 128, 0, s>>>(in, ips, width, in_row0, out, ops, out_row0, out_rows, t.dleft, t.dw);
+}
+static bool vdense_dispatch(const float* in, size_t ips, unsigned width, unsigned in_row0, float* out, size_t ops,
+                            unsigned out_row0, unsigned out_rows, unsigned nplanes, const AxisTableDev& t, cudaStream_t s)
+{
+    switch (t.win) {
+        case 3: launch_vdense<3>(in, ips, width, in_row0, out, ops, out_row0, out_rows, nplanes, t, s); return true;
+        case 5: launch_vdense<5>(in, ips, width, in_row0, out, ops, out_row0, out_rows, nplanes, t, s); return true;
+        case 7: launch_vdense<7>(in, ips, width, in_row0, out, ops, out_row0, out_rows, nplanes, t, s); return true;
+        default: return false;
+    }
+}
+
 void launch_resize_vertical(const float* in, size_t in_plane_stride, unsigned width, unsigned in_row0,
                             float* out, size_t out_plane_stride, unsigned out_row0, unsigned out_rows,
                             unsigned nplanes, AxisTableDev ty, AxisTableDev tc, cudaStream_t s)
 {
     const bool vec = (width % 4 == 0) && (in_plane_stride % 4 == 0) && (out_plane_stride % 4 == 0) &&
                      ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
-    if (vec) {
+    const bool dense = vec && ty.dleft && tc.dleft && (ty.win == 3 || ty.win == 5 || ty.win == 7) &&
+                       (tc.win == 3 || tc.win == 5 || tc.win == 7);
+    if (dense) {
+        /* plane 0 with its own filter, then the remaining planes together */
+        vdense_dispatch(in, in_plane_stride, width, in_row0, out, out_plane_stride, out_row0, out_rows, 1, ty, s);
+        if (nplanes > 1)
+            vdense_dispatch(in + in_plane_stride, in_plane_stride, width, in_row0, out + out_plane_stride, out_plane_stride,
+                            out_row0, out_rows, nplanes - 1, tc, s);
+    } else if (vec) {
         dim3 grid((width / 4 + 127) / 128, out_rows, nplanes);
         resize_vertical_kernel<4><<<grid, 128, 0, s>>>(in, in_plane_stride, width, in_row0, out, out_plane_stride,
                                                        out_row0, out_rows, ty, tc);
@@ -70,7 +126,7 @@ void launch_resize_vertical(const float* in, size_t in_plane_stride, unsigned wi
     }
 }
 
-/* horizontal: thread = one destination sample; a warp reads a short contiguous run of the source row */
+/* horizontal, generic (any window, e.g. minification): thread = one destination sample */
 __global__ void __launch_bounds__(256)
 resize_horizontal_kernel(const float* __restrict__ in, size_t in_plane_stride, unsigned sw,
                          float* __restrict__ out, size_t out_plane_stride, unsigned dw, unsigned rows,
@@ -90,12 +146,66 @@ resize_horizontal_kernel(const float* __restrict__ in, size_t in_plane_stride, u
     out[pl * out_plane_stride + (size_t)yy * dw + x] = __double2float_rn(acc);
 }
 
+/* horizontal, dense table with exactly W taps: thread = one destination column, HROWS rows.  The column's taps are
+ * loaded once into registers and reused down the rows; inner loop = one pixel load + F2F + DMUL + DADD per tap. */
+constexpr int HROWS = 16;
+template <int W>
+__global__ void __launch_bounds__(128)
+resize_horizontal_dense_kernel(const float* __restrict__ in, size_t in_plane_stride, unsigned sw,
+                               float* __restrict__ out, size_t out_plane_stride, unsigned dw, unsigned rows,
+                               const int* __restrict__ dleft, const double* __restrict__ dwt)
+{
+    const unsigned x  = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned y0 = blockIdx.y * HROWS;
+    const unsigned pl = blockIdx.z;
+    if (x >= dw) return;
+    const int left = __ldg(dleft + x);
+    double w[W];
+    #pragma unroll
+    for (int i = 0; i < W; i++) w[i] = __ldg(dwt + (size_t)x * W + i);
+    const float* src = in + pl * in_plane_stride + (size_t)y0 * sw + left;
+    float* dst = out + pl * out_plane_stride + (size_t)y0 * dw + x;
+    const unsigned ny = min((unsigned)HROWS, rows - y0);
+    for (unsigned r = 0; r < ny; r++, src += sw, dst += dw) {
+        double acc = 0.0;
+        #pragma unroll
+        for (int i = 0; i < W; i++) acc = __dadd_rn(acc, __dmul_rn(w[i], (double)__ldg(src + i)));
+        *dst = __double2float_rn(acc);
+    }
+}
+
+template <int W>
+static void launch_hdense(const float* in, size_t ips, unsigned sw, float* out, size_t ops, unsigned dw, unsigned rows,
+                          unsigned nplanes, const AxisTableDev& t, cudaStream_t s)
+{
+    dim3 grid((dw + 127) / 128, (rows + HROWS - 1) / HROWS, nplanes);
+    resize_horizontal_dense_kernel<W><<<grid, 128, 0, s>>>(in, ips, sw, out, ops, dw, rows, t.dleft, t.dw);
+}
+static void hdense_dispatch(const float* in, size_t ips, unsigned sw, float* out, size_t ops, unsigned dw, unsigned rows,
+                            unsigned nplanes, const AxisTableDev& t, cudaStream_t s)
+{
+    switch (t.win) {
+        case 3: launch_hdense<3>(in, ips, sw, out, ops, dw, rows, nplanes, t, s); break;
+        case 5: launch_hdense<5>(in, ips, sw, out, ops, dw, rows, nplanes, t, s); break;
+        default: launch_hdense<7>(in, ips, sw, out, ops, dw, rows, nplanes, t, s); break;
+    }
+}
+
 void launch_resize_horizontal(const float* in, size_t in_plane_stride, unsigned sw,
                               float* out, size_t out_plane_stride, unsigned dw, unsigned rows,
                               unsigned nplanes, AxisTableDev ty, AxisTableDev tc, cudaStream_t s)
 {
-    dim3 grid((dw + 255) / 256, rows, nplanes);
-    resize_horizontal_kernel<<<grid, 256, 0, s>>>(in, in_plane_stride, sw, out, out_plane_stride, dw, rows, ty, tc);
+    const bool dense = ty.dleft && tc.dleft && (ty.win == 3 || ty.win == 5 || ty.win == 7) &&
+                       (tc.win == 3 || tc.win == 5 || tc.win == 7);
+    if (dense) {
+        hdense_dispatch(in, in_plane_stride, sw, out, out_plane_stride, dw, rows, 1, ty, s);
+        if (nplanes > 1)
+            hdense_dispatch(in + in_plane_stride, in_plane_stride, sw, out + out_plane_stride, out_plane_stride, dw, rows,
+                            nplanes - 1, tc, s);
+    } else {
+        dim3 grid((dw + 255) / 256, rows, nplanes);
+        resize_horizontal_kernel<<<grid, 256, 0, s>>>(in, in_plane_stride, sw, out, out_plane_stride, dw, rows, ty, tc);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */

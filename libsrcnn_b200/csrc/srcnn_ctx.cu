@@ -106,13 +106,19 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     TableDev* t = new TableDev;
     build_axis_table(filter, dst, src, t->host);
     const size_t ints = (size_t)dst * sizeof(int);
-    const size_t ints_al = (2 * ints + 15) / 16 * 16;
-    const size_t bytes = ints_al + t->host.w.size() * sizeof(double);
+    const size_t nints = t->host.dense ? 3 : 2;
+    const size_t ints_al = (nints * ints + 15) / 16 * 16;
+    const size_t wbytes = t->host.w.size() * sizeof(double);
+    const size_t bytes = ints_al + wbytes * (t->host.dense ? 2 : 1);
     std::vector<unsigned char> img(bytes, 0);
     int* L = reinterpret_cast<int*>(img.data());
     int* C = L + dst;
     for (unsigned u = 0; u < dst; u++) { L[u] = t->host.left[u]; C[u] = t->host.right[u] - t->host.left[u] + 1; }
-    memcpy(img.data() + ints_al, t->host.w.data(), t->host.w.size() * sizeof(double));
+    memcpy(img.data() + ints_al, t->host.w.data(), wbytes);
+    if (t->host.dense) {
+        memcpy(C + dst, t->host.dleft.data(), ints);
+        memcpy(img.data() + ints_al + wbytes, t->host.dw.data(), wbytes);
+    }
     cudaError_t e = cudaMalloc(&t->dev, bytes);
     if (e != cudaSuccess) { delete t; return fail_cuda(ctx, e, "cudaMalloc(table)"); }
     e = cudaMemcpyAsync(t->dev, img.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
@@ -122,9 +128,23 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     t->view.count = t->view.left + dst;
     t->view.w     = reinterpret_cast<const double*>(static_cast<unsigned char*>(t->dev) + ints_al);
     t->view.win   = t->host.win;
+    t->view.dleft = t->host.dense ? t->view.count + dst : nullptr;
+    t->view.dw    = t->host.dense ? t->view.w + t->host.w.size() : nullptr;
     ctx->tables[key] = t;
     *out = t;
     return 0;
+}
+
+/* source rows read by the vertical pass for destination rows [e0,e1): the dense windows when the tables have them */
+void source_rows(const AxisTable& a, const AxisTable& b, unsigned e0, unsigned e1, unsigned& s0, unsigned& s1)
+{
+    int lo = INT32_MAX, hi = -1;
+    for (const AxisTable* t : { &a, &b })
+        for (unsigned r = e0; r < e1; r++) {
+            lo = std::min(lo, t->left[r]); hi = std::max(hi, t->right[r]);
+            if (t->dense) { lo = std::min(lo, t->dleft[r]); hi = std::max(hi, t->dleft[r] + t->win - 1); }
+        }
+    s0 = (unsigned)lo; s1 = (unsigned)hi + 1;
 }
 
 int make_plan(unsigned w, unsigned h, unsigned d, float multiply, int filter, unsigned row0, unsigned row1, Plan& p)
@@ -161,12 +181,7 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, bool src_i
     if (p.need_v) {
         if ((rc = get_table(ctx, p.fy, p.oh, p.h, &vy))) return rc;
         if ((rc = get_table(ctx, p.fc, p.oh, p.h, &vc))) return rc;
-        int lo = INT32_MAX, hi = -1;
-        for (unsigned r = p.e0; r < p.e1; r++) {
-            lo = std::min(lo, std::min(vy->host.left[r], vc->host.left[r]));
-            hi = std::max(hi, std::max(vy->host.right[r], vc->host.right[r]));
-        }
-        p.s0 = (unsigned)lo; p.s1 = (unsigned)hi + 1;
+        source_rows(vy->host, vc->host, p.e0, p.e1, p.s0, p.s1);
     } else { p.s0 = p.e0; p.s1 = p.e1; }
     if (p.need_h) {
         if ((rc = get_table(ctx, p.fy, p.ow, p.w, &hy))) return rc;
@@ -422,12 +437,7 @@ int srcnn_b200_pass_host_rows(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned 
         if (p.need_v) {
             if ((rc = get_table(ctx, p.fy, p.oh, p.h, &vy))) return rc;
             if ((rc = get_table(ctx, p.fc, p.oh, p.h, &vc))) return rc;
-            int lo = INT32_MAX, hi = -1;
-            for (unsigned r = p.e0; r < p.e1; r++) {
-                lo = std::min(lo, std::min(vy->host.left[r], vc->host.left[r]));
-                hi = std::max(hi, std::max(vy->host.right[r], vc->host.right[r]));
-            }
-            p.s0 = (unsigned)lo; p.s1 = (unsigned)hi + 1;
+            source_rows(vy->host, vc->host, p.e0, p.e1, p.s0, p.s1);
         } else { p.s0 = p.e0; p.s1 = p.e1; }
     }
     const size_t in_bytes = (size_t)(p.s1 - p.s0) * w * d;
