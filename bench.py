@@ -32,6 +32,7 @@ ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
+NCU_CONV_DRAM_BYTES = 17079808   # conv_tc_kernel at C2: 17.02 MB read + 0.06 MB written (profiles/r1_ncu_summary.md)
 FLOP_PER_PX = 16064            # conv I 81*64 + conv II 64*32 + conv III 25*32 MACs, x2
 WORKLOADS = {
     # name: (h, w, d, multiply, filter, description)
@@ -257,7 +258,9 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "fused conv I+II+III (%s)" % args.conv, "bound": "tensor", "achieved": achieved_tf,
-                     "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf"], "traffic": None,
+                     "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf"],
+                     "traffic": NCU_CONV_DRAM_BYTES if (args.workload == "c2" and args.conv == "tensor") else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r1_ncu_summary.md); the 33 MB Y' write stays in L2",
                      "peak_source": pk["src"], "kernel_ms": conv_avg_ms,
                      "algorithmic_flop_per_launch": out_px * FLOP_PER_PX},
         "stage_ms": stage_avg,

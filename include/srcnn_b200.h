@@ -68,6 +68,12 @@ int srcnn_b200_pass_host_rows(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned 
                               float multiply, int filter, unsigned row0, unsigned row1,
                               uint8_t* out_rows, uint8_t* conv_rows);
 
+/* Host-side geometry of a strip (no GPU needed): the rows [*halo_row0,*halo_row1) of the interpolated planes the strip
+ * computes (strip +- 6 clipped to the image) and the source rows [*src_row0,*src_row1) it reads / uploads. */
+int srcnn_b200_strip_geometry(unsigned w, unsigned h, unsigned d, float multiply, int filter,
+                              unsigned row0, unsigned row1, unsigned* halo_row0, unsigned* halo_row1,
+                              unsigned* src_row0, unsigned* src_row1);
+
 /* Device-resident variant: d_src (whole image), d_out / d_conv (rows [row0,row1), d_conv may be NULL) are DEVICE
  * pointers on the context's device.  Work is enqueued on the context's stream; call srcnn_b200_sync (or use
  * srcnn_b200_stream) to order against it.  This is the kernel-throughput path the benchmark times. */

@@ -48,6 +48,7 @@ def lib():
         L.srcnn_b200_get_conv_mode.argtypes = [vp]
         L.srcnn_b200_output_dims.argtypes = [u, u, f, C.POINTER(u), C.POINTER(u)]; L.srcnn_b200_output_dims.restype = None
         L.srcnn_b200_process_dims.argtypes = [u, u, f, i, C.POINTER(u), C.POINTER(u)]
+        L.srcnn_b200_strip_geometry.argtypes = [u, u, u, f, i, u, u] + [C.POINTER(u)] * 4
         L.srcnn_b200_pass_host.argtypes = [vp, vp, u, u, u, f, i, vp, vp]
         L.srcnn_b200_pass_host_rows.argtypes = [vp, vp, u, u, u, f, i, u, u, vp, vp]
         L.srcnn_b200_pass_device.argtypes = [vp, vp, u, u, u, f, i, u, u, vp, vp]
@@ -87,6 +88,21 @@ def process_dims(w, h, multiply, stepscale):
     ow, oh = C.c_uint(), C.c_uint()
     n = lib().srcnn_b200_process_dims(w, h, multiply, int(bool(stepscale)), C.byref(ow), C.byref(oh))
     return n, ow.value, oh.value
+
+
+def strip_rows(total_rows, parts, index):
+    """rows [a, b) of strip `index` when an image of `total_rows` output rows is cut into `parts` row strips
+    (the sharding rule of the multi-GPU drivers: contiguous, balanced, disjoint, covering)"""
+    return (index * total_rows) // parts, ((index + 1) * total_rows) // parts
+
+
+def strip_geometry(w, h, d, multiply, filt, row0, row1):
+    """-> (halo_rows (a, b) of the interpolated planes, source rows (a, b) read) for the strip [row0, row1)"""
+    v = [C.c_uint() for _ in range(4)]
+    rc = lib().srcnn_b200_strip_geometry(w, h, d, multiply, int(filt), row0, row1, *[C.byref(x) for x in v])
+    if rc != 0:
+        raise SrcnnError(rc, "strip_geometry")
+    return (v[0].value, v[1].value), (v[2].value, v[3].value)
 
 
 def contrib_table(filt, dst, src, maxwin=64):

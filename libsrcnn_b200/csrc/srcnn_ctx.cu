@@ -403,6 +403,23 @@ int srcnn_b200_process_dims(unsigned w, unsigned h, float multiply, int stepscal
     return n;
 }
 
+int srcnn_b200_strip_geometry(unsigned w, unsigned h, unsigned d, float multiply, int filter,
+                              unsigned row0, unsigned row1, unsigned* halo_row0, unsigned* halo_row1,
+                              unsigned* src_row0, unsigned* src_row1)
+{
+    Plan p; int rc = make_plan(w, h, d, multiply, filter, row0, row1, p);
+    if (rc) return rc;
+    if (p.need_v) {
+        AxisTable vy, vc;
+        build_axis_table(p.fy, p.oh, p.h, vy);
+        build_axis_table(p.fc, p.oh, p.h, vc);
+        source_rows(vy, vc, p.e0, p.e1, p.s0, p.s1);
+    } else { p.s0 = p.e0; p.s1 = p.e1; }
+    if (halo_row0) *halo_row0 = p.e0; if (halo_row1) *halo_row1 = p.e1;
+    if (src_row0) *src_row0 = p.s0; if (src_row1) *src_row1 = p.s1;
+    return 0;
+}
+
 int srcnn_b200_pass_device(srcnn_b200_ctx* ctx, const void* d_src, unsigned w, unsigned h, unsigned d,
                            float multiply, int filter, unsigned row0, unsigned row1, void* d_out, void* d_conv)
 {
