@@ -119,9 +119,14 @@ def _vp(a):
     return C.c_void_p(a.ctypes.data) if a is not None else None
 
 
-def process_srcnn(img, multiply, filt=BICUBIC, stepscale=False, want_conv=True):
+_dele = None
+
+
+def process_srcnn(img, multiply, filt=BICUBIC, stepscale=False, want_conv=True, copy=True):
     """The drop-in C++ API exactly as an application calls it: ConfigureFilterSRCNN + ProcessSRCNN.
-    -> (rc, out | None, conv | None); the new[] buffers are copied and released via libstdc++'s operator delete[]."""
+    -> (rc, out | None, conv | None); the new[] buffers are copied and released via libstdc++'s operator delete[].
+    copy=False (timing): the buffers are released without being copied into numpy arrays -> (rc, size, conv size)."""
+    global _dele
     L = lib()
     h, w, d = img.shape
     img = np.ascontiguousarray(img, np.uint8)
@@ -130,8 +135,16 @@ def process_srcnn(img, multiply, filt=BICUBIC, stepscale=False, want_conv=True):
     rc = L.ProcessSRCNN(_vp(img), w, h, d, C.c_float(multiply), C.byref(out), C.byref(osz),
                         C.byref(cv) if want_conv else None, C.byref(csz) if want_conv else None)
     o = c = None
-    dele = C.CDLL("libstdc++.so.6")._ZdaPv          # operator delete[](void*)
-    dele.argtypes = [C.c_void_p]; dele.restype = None
+    if _dele is None:
+        _dele = C.CDLL("libstdc++.so.6")._ZdaPv     # operator delete[](void*)
+        _dele.argtypes = [C.c_void_p]; _dele.restype = None
+    dele = _dele
+    if not copy:
+        if out.value:
+            dele(out)
+        if cv.value:
+            dele(cv)
+        return rc, osz.value, csz.value
     if out.value:
         o = np.ctypeslib.as_array(C.cast(out, _u8p), (osz.value,)).copy(); dele(out)
     if cv.value:

@@ -17,6 +17,10 @@
 #include <string>
 #include <tuple>
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 using namespace srcnn;
 
@@ -48,6 +52,61 @@ struct PinBuf {
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
+
+/* host-side memcpy spread over a few persistent worker threads (pinned staging -> the caller's pageable rows) */
+class HostCopier {
+public:
+    ~HostCopier() { stop(); }
+    void start(unsigned workers)
+    {
+        if (!th_.empty() || workers == 0) return;
+        for (unsigned i = 0; i < workers; i++) th_.emplace_back([this, i] { loop(i); });
+    }
+    void stop()
+    {
+        { std::lock_guard<std::mutex> g(m_); quit_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+        th_.clear(); quit_ = false;
+    }
+    void copy(unsigned char* dst, const unsigned char* src, size_t n)
+    {
+        const size_t parts = th_.size() + 1;
+        if (parts == 1 || n < (size_t)256 << 10) { memcpy(dst, src, n); return; }
+        const size_t slice = ((n + parts - 1) / parts + 4095) / 4096 * 4096;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            dst_ = dst; src_ = src; n_ = n; slice_ = slice; pending_ = (unsigned)th_.size(); gen_++;
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(slice, n));                                   /* the caller takes slice 0 */
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return pending_ == 0; });
+    }
+private:
+    void loop(unsigned id)
+    {
+        unsigned long seen = 0;
+        for (;;) {
+            unsigned char* d; const unsigned char* s; size_t n, sl;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return quit_ || gen_ != seen; });
+                if (quit_) return;
+                seen = gen_; d = dst_; s = src_; n = n_; sl = slice_;
+            }
+            const size_t a = (size_t)(id + 1) * sl;
+            if (a < n) memcpy(d + a, s + a, std::min(sl, n - a));
+            { std::lock_guard<std::mutex> g(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_; std::condition_variable cv_, done_;
+    unsigned char* dst_ = nullptr; const unsigned char* src_ = nullptr; size_t n_ = 0, slice_ = 0;
+    unsigned pending_ = 0; unsigned long gen_ = 0; bool quit_ = false;
+};
+
+constexpr unsigned kMaxPipeStrips = 32, kStageSlots = 3;
 
 struct TableDev {
     AxisTable host;
@@ -83,6 +142,11 @@ struct srcnn_b200_ctx {
     float ms[7] = {};
     unsigned long long launches = 0;
     std::string err;
+    /* host pipeline (srcnn_b200_pass_host_rows) */
+    size_t strip_bytes = (size_t)8 << 20;     /* result bytes per pipelined sub-strip (SRCNN_B200_STRIP_MB)          */
+    bool stage_pageable = true;               /* pageable results go through pinned staging (SRCNN_B200_STAGE=0: off) */
+    std::vector<cudaEvent_t> pipe_ev;         /* 3 per sub-strip: uploaded, computed, downloaded                      */
+    HostCopier copier;
     /* last pass, for the plane getters */
     Plan last{}; bool have_last = false; size_t last_plane_stride = 0;
 };
@@ -97,6 +161,24 @@ int fail_cuda(srcnn_b200_ctx* c, cudaError_t e, const char* what)
     return SRCNN_B200_ECUDA;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call); } while (0)
+
+bool host_is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+cudaError_t ensure_pipe_events(srcnn_b200_ctx* c, unsigned nstrips)
+{
+    while (c->pipe_ev.size() < (size_t)3 * nstrips) {
+        cudaEvent_t e;
+        cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        if (r != cudaSuccess) return r;
+        c->pipe_ev.push_back(e);
+    }
+    return cudaSuccess;
+}
 
 int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, TableDev** out)
 {
@@ -172,8 +254,10 @@ struct Stamp {
     void mark() { if (c->timing && i < 8) cudaEventRecord(c->ev[i], c->stream); i++; }
 };
 
-/* d_src points at source row p.s0 (device); d_out/d_conv at output row p.r0 (device).  Asynchronous. */
-int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, bool src_is_whole_image,
+/* d_src_base points at source row `src_base_row` (device; kWholeImage = row 0, kStripRows = row p.s0);
+ * d_out/d_conv at output row p.r0 (device).  Asynchronous on ctx->stream. */
+constexpr long kStripRows = -1;
+int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_base_row,
              uint8_t* d_out, uint8_t* d_conv)
 {
     TableDev *vy = nullptr, *vc = nullptr, *hy = nullptr, *hc = nullptr;
@@ -187,7 +271,8 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, bool src_i
         if ((rc = get_table(ctx, p.fy, p.ow, p.w, &hy))) return rc;
         if ((rc = get_table(ctx, p.fc, p.ow, p.w, &hc))) return rc;
     }
-    const uint8_t* d_src = src_is_whole_image ? d_src_base + (size_t)p.s0 * p.w * p.d : d_src_base;
+    const uint8_t* d_src = src_base_row == kStripRows ? d_src_base
+                                                      : d_src_base + ((size_t)p.s0 - (size_t)src_base_row) * p.w * p.d;
 
     const unsigned srows = p.s1 - p.s0, erows = p.e1 - p.e0, orows = p.r1 - p.r0;
     auto al = [](size_t n) { return (n + 63) / 64 * 64; };
@@ -311,6 +396,13 @@ int srcnn_b200_create(int device, srcnn_b200_ctx** out)
     srcnn_b200_ctx* ctx = new srcnn_b200_ctx;
     ctx->device = device; ctx->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SRCNN_B200_CHAIN")) ctx->chain_tensor = (strcmp(e, "tensor") == 0);
+    if (const char* e = getenv("SRCNN_B200_STRIP_MB")) { const double mb = atof(e); if (mb >= 0.25) ctx->strip_bytes = (size_t)(mb * 1048576.0); }
+    if (const char* e = getenv("SRCNN_B200_STAGE")) ctx->stage_pageable = atoi(e) != 0;
+    {
+        unsigned nt = std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        if (const char* e = getenv("SRCNN_B200_COPY_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+        ctx->copier.start(nt - 1);
+    }
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -346,6 +438,8 @@ void srcnn_b200_destroy(srcnn_b200_ctx* ctx)
     }
     ctx->planes_src.release(); ctx->tmp.release(); ctx->planes_dst.release(); ctx->y16.release(); ctx->yprime.release();
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
+    ctx->copier.stop();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
     if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
@@ -427,7 +521,7 @@ int srcnn_b200_pass_device(srcnn_b200_ctx* ctx, const void* d_src, unsigned w, u
     Plan p; int rc = make_plan(w, h, d, multiply, filter, row0, row1, p);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    return run_pass(ctx, p, static_cast<const uint8_t*>(d_src), true, static_cast<uint8_t*>(d_out),
+    return run_pass(ctx, p, static_cast<const uint8_t*>(d_src), 0, static_cast<uint8_t*>(d_out),
                     static_cast<uint8_t*>(d_conv));
 }
 
@@ -448,29 +542,93 @@ int srcnn_b200_pass_host_rows(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned 
     Plan p; int rc = make_plan(w, h, d, multiply, filter, row0, row1, p);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    /* source rows needed: resolve the vertical tables first (run_pass repeats the lookup from the cache) */
-    {
-        TableDev *vy, *vc;
-        if (p.need_v) {
-            if ((rc = get_table(ctx, p.fy, p.oh, p.h, &vy))) return rc;
-            if ((rc = get_table(ctx, p.fc, p.oh, p.h, &vc))) return rc;
-            source_rows(vy->host, vc->host, p.e0, p.e1, p.s0, p.s1);
-        } else { p.s0 = p.e0; p.s1 = p.e1; }
+    TableDev *vy = nullptr, *vc = nullptr;
+    if (p.need_v) {
+        if ((rc = get_table(ctx, p.fy, p.oh, p.h, &vy))) return rc;
+        if ((rc = get_table(ctx, p.fc, p.oh, p.h, &vc))) return rc;
     }
-    const size_t in_bytes = (size_t)(p.s1 - p.s0) * w * d;
-    const size_t out_bytes = (size_t)(row1 - row0) * p.ow * d, conv_bytes = (size_t)(row1 - row0) * p.ow;
-    CK(ctx->src8[0].ensure(in_bytes));
+    /* The call is cut into row sub-strips that flow through a three-stage pipeline
+     *     upload source rows (stream_in) | kernels (stream) | download result rows (stream_out)
+     * so the PCIe transfers of one sub-strip hide behind the kernels of its neighbours.  Sub-strips are ordinary
+     * row strips (6-row halo recomputed), hence bit-identical to the one-shot result.  The whole source row range
+     * and the whole result live in device buffers: overlapping source rows are uploaded once, nothing is reused
+     * while in flight. */
+    const size_t row_bytes = (size_t)p.ow * d;
+    const size_t out_bytes = (size_t)(row1 - row0) * row_bytes, conv_bytes = (size_t)(row1 - row0) * p.ow;
+    unsigned nstrips = (unsigned)std::min<size_t>((out_bytes + ctx->strip_bytes / 2) / ctx->strip_bytes, kMaxPipeStrips);
+    nstrips = std::max(1u, std::min(nstrips, (row1 - row0) / 64u));
+    Plan sp[kMaxPipeStrips];
+    for (unsigned i = 0; i < nstrips; i++) {
+        const unsigned a = row0 + (unsigned)((size_t)(row1 - row0) * i / nstrips);
+        const unsigned b = row0 + (unsigned)((size_t)(row1 - row0) * (i + 1) / nstrips);
+        if ((rc = make_plan(w, h, d, multiply, filter, a, b, sp[i]))) return rc;
+        if (p.need_v) source_rows(vy->host, vc->host, sp[i].e0, sp[i].e1, sp[i].s0, sp[i].s1);
+        else { sp[i].s0 = sp[i].e0; sp[i].s1 = sp[i].e1; }
+    }
+    const unsigned S0 = sp[0].s0, S1 = sp[nstrips - 1].s1;
+    const size_t src_row_bytes = (size_t)w * d;
+    CK(ctx->src8[0].ensure((size_t)(S1 - S0) * src_row_bytes));
     CK(ctx->out8[0].ensure(out_bytes));
     if (conv_rows) CK(ctx->conv8[0].ensure(conv_bytes));
-    CK(cudaMemcpyAsync(ctx->src8[0].p, src + (size_t)p.s0 * w * d, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    rc = run_pass(ctx, p, static_cast<const uint8_t*>(ctx->src8[0].p), false, static_cast<uint8_t*>(ctx->out8[0].p),
-                  conv_rows ? static_cast<uint8_t*>(ctx->conv8[0].p) : nullptr);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(out_rows, ctx->out8[0].p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (conv_rows) CK(cudaMemcpyAsync(conv_rows, ctx->conv8[0].p, conv_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    uint8_t* d_src = static_cast<uint8_t*>(ctx->src8[0].p);
+    uint8_t* d_out = static_cast<uint8_t*>(ctx->out8[0].p);
+    uint8_t* d_conv = conv_rows ? static_cast<uint8_t*>(ctx->conv8[0].p) : nullptr;
+
+    /* pageable destination: DMA into pinned staging slots, worker threads move the rows on (a cudaMemcpy straight
+     * into pageable memory is staged by the driver in small chunks and blocks the pipeline) */
+    const bool stage = ctx->stage_pageable && nstrips > 1 && !host_is_pinned(out_rows);
+    size_t slot_bytes = 0;
+    if (stage) {
+        for (unsigned i = 0; i < nstrips; i++)
+            slot_bytes = std::max(slot_bytes, (size_t)(sp[i].r1 - sp[i].r0) * (row_bytes + (conv_rows ? p.ow : 0)));
+        slot_bytes = (slot_bytes + 4095) / 4096 * 4096;
+        CK(ctx->pin_out[0].ensure(slot_bytes * kStageSlots));
+    }
+    CK(ensure_pipe_events(ctx, nstrips));
+
+    auto drain = [&](unsigned j) -> int {      /* staging slot j % kStageSlots -> caller's rows */
+        CK(cudaEventSynchronize(ctx->pipe_ev[3 * j + 2]));
+        const unsigned char* slot = static_cast<unsigned char*>(ctx->pin_out[0].p) + (size_t)(j % kStageSlots) * slot_bytes;
+        const size_t ob = (size_t)(sp[j].r1 - sp[j].r0) * row_bytes, off = (size_t)(sp[j].r0 - row0);
+        ctx->copier.copy(out_rows + off * row_bytes, slot, ob);
+        if (conv_rows) ctx->copier.copy(conv_rows + off * p.ow, slot + ob, (size_t)(sp[j].r1 - sp[j].r0) * p.ow);
+        return 0;
+    };
+
+    unsigned uploaded = S0;
+    for (unsigned i = 0; i < nstrips; i++) {
+        cudaEvent_t ev_in = ctx->pipe_ev[3 * i], ev_k = ctx->pipe_ev[3 * i + 1], ev_out = ctx->pipe_ev[3 * i + 2];
+        if (sp[i].s1 > uploaded) {
+            CK(cudaMemcpyAsync(d_src + (size_t)(uploaded - S0) * src_row_bytes, src + (size_t)uploaded * src_row_bytes,
+                               (size_t)(sp[i].s1 - uploaded) * src_row_bytes, cudaMemcpyHostToDevice, ctx->stream_in));
+            uploaded = sp[i].s1;
+        }
+        CK(cudaEventRecord(ev_in, ctx->stream_in));
+        CK(cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+        const size_t off = (size_t)(sp[i].r0 - row0);
+        rc = run_pass(ctx, sp[i], d_src, (long)S0, d_out + off * row_bytes, d_conv ? d_conv + off * p.ow : nullptr);
+        if (rc) return rc;
+        CK(cudaEventRecord(ev_k, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream_out, ev_k, 0));
+        const size_t ob = (size_t)(sp[i].r1 - sp[i].r0) * row_bytes, cb = (size_t)(sp[i].r1 - sp[i].r0) * p.ow;
+        if (stage) {
+            if (i >= kStageSlots && (rc = drain(i - kStageSlots))) return rc;      /* slot free again */
+            unsigned char* slot = static_cast<unsigned char*>(ctx->pin_out[0].p) + (size_t)(i % kStageSlots) * slot_bytes;
+            CK(cudaMemcpyAsync(slot, d_out + off * row_bytes, ob, cudaMemcpyDeviceToHost, ctx->stream_out));
+            if (conv_rows) CK(cudaMemcpyAsync(slot + ob, d_conv + off * p.ow, cb, cudaMemcpyDeviceToHost, ctx->stream_out));
+        } else {
+            CK(cudaMemcpyAsync(out_rows + off * row_bytes, d_out + off * row_bytes, ob, cudaMemcpyDeviceToHost, ctx->stream_out));
+            if (conv_rows) CK(cudaMemcpyAsync(conv_rows + off * p.ow, d_conv + off * p.ow, cb, cudaMemcpyDeviceToHost, ctx->stream_out));
+        }
+        CK(cudaEventRecord(ev_out, ctx->stream_out));
+    }
+    if (stage)
+        for (unsigned j = nstrips > kStageSlots ? nstrips - kStageSlots : 0; j < nstrips; j++)
+            if ((rc = drain(j))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream_out));
     CK(cudaStreamSynchronize(ctx->stream));
     collect_timing(ctx);
-    return 0;
+    return 0;                                 /* (the plane getters describe the last sub-strip) */
 }
 
 int srcnn_b200_pass_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
@@ -519,7 +677,7 @@ int srcnn_b200_process_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w,
         { cudaError_t e1 = ctx->chain[cur ^ 1].ensure(ob);
           if (e1 == cudaSuccess && last && conv) e1 = ctx->conv8[0].ensure((size_t)p.ow * p.oh);
           if (e1 != cudaSuccess) { ctx->conv_mode = saved_mode; return fail_cuda(ctx, e1, "chain buffers"); } }
-        rc = run_pass(ctx, p, static_cast<const uint8_t*>(ctx->chain[cur].p), true,
+        rc = run_pass(ctx, p, static_cast<const uint8_t*>(ctx->chain[cur].p), 0,
                       static_cast<uint8_t*>(ctx->chain[cur ^ 1].p),
                       (last && conv) ? static_cast<uint8_t*>(ctx->conv8[0].p) : nullptr);
         ctx->conv_mode = saved_mode;
@@ -556,7 +714,7 @@ int srcnn_b200_batch_host(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
         if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));       /* out8[b] drained by frame i-2 */
         Plan p; make_plan(w, h, d, multiply, filter, 0, p0.oh, p);
-        rc = run_pass(ctx, p, static_cast<const uint8_t*>(ctx->src8[b].p), true, static_cast<uint8_t*>(ctx->out8[b].p),
+        rc = run_pass(ctx, p, static_cast<const uint8_t*>(ctx->src8[b].p), 0, static_cast<uint8_t*>(ctx->out8[b].p),
                       conv ? static_cast<uint8_t*>(ctx->conv8[b].p) : nullptr);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_k[b], ctx->stream));
