@@ -103,6 +103,9 @@ void  srcnn_b200_host_free(void* p);
  * 4 network output Y'.  Planes 0-3 cover the strip's extended rows [*row0, *row0 + *rows); plane 4 the strip rows. */
 int srcnn_b200_get_plane(srcnn_b200_ctx* ctx, int which, float* host, size_t cap,
                          unsigned* row0, unsigned* rows, unsigned* width);
+/* The tensor-core path consumes the interpolated Y plane as FP16 and never writes its FP32 form to HBM.  Switch this
+ * on (before the pass) to have plane 0 written as well, for srcnn_b200_get_plane(ctx, 0, ...).  Default off. */
+int srcnn_b200_set_keep_planes(srcnn_b200_ctx* ctx, int on);
 /* GPU time (ms, CUDA events on the context's stream) of the LAST pass's kernels:
  * [0] colour-in [1] resize pass 1 [2] resize pass 2 [3] conv-input pack [4] fused conv [5] colour-out [6] total.
  * Only recorded while srcnn_b200_set_timing(ctx, 1). */
@@ -127,6 +130,13 @@ int srcnn_b200_stage_color_out(srcnn_b200_ctx* ctx, const float* const* planes, 
  * Returns the window size, or -1 if maxwin is too small. */
 int srcnn_b200_contrib_table(int filter, unsigned dst, unsigned src, int* left, int* right,
                              double* weights, int maxwin);
+
+/* The compact form of the same table that the fused front-end kernel reads: per destination index `cwin` in-bounds
+ * taps starting at cleft, with the exactly-zero weights of the reference's window trimmed away (adding +-0 to the
+ * accumulator changes nothing).  *exact29 = 1 if every weight has <= 29 significant bits (its product with an FP32
+ * sample is then exact in double).  Returns cwin, 0 if the source is narrower than the window, -1 if maxwin is too small. */
+int srcnn_b200_contrib_table_compact(int filter, unsigned dst, unsigned src, int* cleft, double* weights, int maxwin,
+                                     int* exact29);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -60,6 +60,7 @@ def lib():
         L.srcnn_b200_host_free.argtypes = [vp]; L.srcnn_b200_host_free.restype = None
         L.srcnn_b200_get_plane.argtypes = [vp, i, vp, C.c_size_t, C.POINTER(u), C.POINTER(u), C.POINTER(u)]
         L.srcnn_b200_set_timing.argtypes = [vp, i]
+        L.srcnn_b200_set_keep_planes.argtypes = [vp, i]
         L.srcnn_b200_last_timings.argtypes = [vp, _f32p]
         L.srcnn_b200_launch_count.argtypes = [vp]; L.srcnn_b200_launch_count.restype = C.c_ulonglong
         L.srcnn_b200_stage_color_in.argtypes = [vp, vp, u, u, u, C.POINTER(vp)]
@@ -67,6 +68,7 @@ def lib():
         L.srcnn_b200_stage_conv.argtypes = [vp, vp, u, u, i, vp]
         L.srcnn_b200_stage_color_out.argtypes = [vp, C.POINTER(vp), u, u, u, vp, vp]
         L.srcnn_b200_contrib_table.argtypes = [i, u, u, _i32p, _i32p, _f64p, i]
+        L.srcnn_b200_contrib_table_compact.argtypes = [i, u, u, _i32p, _f64p, i, _i32p]
         # the C++ drop-in API, by its (reference-identical) mangled names
         L.ProcessSRCNN = getattr(L, "_Z12ProcessSRCNNPKhjjjfRPhRjPS1_Pj")
         L.ProcessSRCNN.restype = i
@@ -113,6 +115,16 @@ def contrib_table(filt, dst, src, maxwin=64):
     if win < 0:
         raise SrcnnError(win, "contrib_table")
     return L, R, W
+
+
+def contrib_table_compact(filt, dst, src, maxwin=16):
+    """compact form read by the fused front-end kernel -> (cwin, cleft, weights[dst, maxwin], exact29); cwin 0 = none"""
+    L = np.zeros(dst, np.int32); W = np.zeros((dst, maxwin), np.float64); ex = C.c_int(0)
+    win = lib().srcnn_b200_contrib_table_compact(int(filt), dst, src, L.ctypes.data_as(_i32p), W.ctypes.data_as(_f64p),
+                                                 maxwin, C.byref(ex))
+    if win < 0:
+        raise SrcnnError(win, "contrib_table_compact")
+    return win, L, W, bool(ex.value)
 
 
 def _vp(a):
@@ -240,6 +252,9 @@ class Context:
         self._ck(self.L.srcnn_b200_get_plane(self.h, which, _vp(buf), buf.size, C.byref(r0), C.byref(nr), C.byref(wd)),
                  "get_plane")
         return r0.value, buf[: nr.value * wd.value].reshape(nr.value, wd.value).copy()
+
+    def set_keep_planes(self, on=True):
+        self._ck(self.L.srcnn_b200_set_keep_planes(self.h, int(on)), "set_keep_planes")
 
     def set_timing(self, on=True):
         self._ck(self.L.srcnn_b200_set_timing(self.h, int(on)), "set_timing")

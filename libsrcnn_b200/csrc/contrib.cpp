@@ -7,6 +7,8 @@
  */
 #include "contrib.h"
 #include <cmath>
+#include <cstdint>
+#include <cstring>
 
 namespace srcnn {
 
@@ -99,6 +101,34 @@ void build_axis_table(int filter, unsigned dst, unsigned src, AxisTable& t)
             if (dl + t.win > (int)src) dl = (int)src - t.win;      /* shift the window left, zero weights in front */
             t.dleft[u] = dl;
             for (int i = t.left[u]; i <= t.right[u]; i++) t.dw[(size_t)u * t.win + (i - dl)] = t.w[(size_t)u * t.win + (i - t.left[u])];
+        }
+    }
+    /* compact form */
+    int widest = 1;
+    std::vector<int> first(dst), lastnz(dst);
+    t.exact29 = true;
+    for (unsigned u = 0; u < dst; u++) {
+        const double* wu = &t.w[(size_t)u * t.win];
+        int a = t.left[u], b = t.right[u];
+        while (a < b && wu[a - t.left[u]] == 0) a++;
+        while (b > a && wu[b - t.left[u]] == 0) b--;
+        first[u] = a; lastnz[u] = b;
+        widest = widest > b - a + 1 ? widest : b - a + 1;
+        for (int i = a; i <= b; i++) {
+            uint64_t bits; const double v = wu[i - t.left[u]];
+            memcpy(&bits, &v, 8);
+            if (v != 0 && (bits & ((1ull << 24) - 1)) != 0) t.exact29 = false;      /* 52 - 28 low mantissa bits clear */
+        }
+    }
+    t.cwin = (widest + 1) / 2 * 2;
+    t.compact = (int)src >= t.cwin;
+    if (t.compact) {
+        t.cleft.assign(dst, 0); t.cw.assign((size_t)dst * t.cwin, 0.0);
+        for (unsigned u = 0; u < dst; u++) {
+            int cl = first[u];
+            if (cl + t.cwin > (int)src) cl = (int)src - t.cwin;
+            t.cleft[u] = cl;
+            for (int i = first[u]; i <= lastnz[u]; i++) t.cw[(size_t)u * t.cwin + (i - cl)] = t.w[(size_t)u * t.win + (i - t.left[u])];
         }
     }
 }

@@ -18,6 +18,15 @@ struct AxisTable {
     bool dense = false;
     std::vector<int>    dleft;
     std::vector<double> dw;
+    /* compact form (only when src >= cwin): like the dense form, but the window is cut down to the widest run of
+     * non-zero weights over all destination indices, rounded up to an even size (2 for box / bilinear, 4 for the
+     * cubics, 6 for Lanczos-3 when magnifying).  Taps with weight exactly 0 add +-0 to the accumulator, i.e. nothing,
+     * so leaving them out is bit-identical.  exact29: every weight has at most 29 significant bits, so its product
+     * with an FP32 sample is exact in double and a fused multiply-add equals the reference's multiply then add. */
+    bool compact = false, exact29 = false;
+    int cwin = 0;
+    std::vector<int>    cleft;
+    std::vector<double> cw;
 };
 
 double filter_support(int filter);

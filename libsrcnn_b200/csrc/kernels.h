@@ -18,6 +18,11 @@ struct AxisTableDev {
     /* dense form (NULL if unavailable): exactly win in-bounds taps from dleft, zero weights where unused */
     const int*    dleft;
     const double* dw;
+    /* compact form (NULL if unavailable): cwin taps from cleft, zero-weight taps trimmed (contrib.h) */
+    const int*    cleft;
+    const double* cw;
+    int           cwin;
+    int           exact29;  /* all weights have <= 29 significant bits: fma == mul, add */
 };
 
 /* geometry of the FP16 conv-input plane consumed by the tensor-core kernel (see DESIGN.md "Y16 plane") */
@@ -47,6 +52,19 @@ void launch_resize_vertical(const float* in, size_t in_plane_stride, unsigned wi
 void launch_resize_horizontal(const float* in, size_t in_plane_stride, unsigned sw,
                               float* out, size_t out_plane_stride, unsigned dw, unsigned rows,
                               unsigned nplanes, AxisTableDev ty, AxisTableDev tc, cudaStream_t s);
+
+/* fused front end (prep.cu): colour-in + vertical + horizontal resampling + conv-input pack in one kernel, for the
+ * upscale order (vertical pass first) with compact tables.  src = device pointer at source row src_row0; planes = d FP32
+ * planes whose row 0 is destination row e0 (plane 0 only written if write_y32); y16 may be NULL (no conv-input plane).
+ * h_* = the host copies of the compact `left` arrays (tile footprints).  Returns 1 if launched, 0 if this geometry is
+ * not covered (the caller then runs the separate kernels). */
+int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, unsigned ow, unsigned oh,
+                unsigned e0, unsigned e1, float* planes, size_t plane_stride, bool write_y32,
+                __half* y16, Y16Geom g, unsigned strip_row0,
+                const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc,
+                const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, cudaStream_t s);
+/* host-side applicability test of launch_prep for a set of tables */
+bool prep_supported(const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc);
 
 /* conv-input pack: FP32 Y window (rows [win_row0, win_row0+win_rows) of a dw x dh plane) -> replicate-padded FP16
  * plane covering global rows strip_row0-6 .. strip_row1+6 (clamped) and columns -8 .. pitch-9 (clamped) */

@@ -1,0 +1,356 @@
+/* Fused front end of one pass: colour-in + both resampling passes + the conv-input pack, one kernel, one trip to HBM.
+ *
+ *   u8 RGB(A) source rows  ->  Cb, Cr, (A) FP32 planes at output size  +  replicate-padded FP16 Y plane (conv input)
+ *                              (+ the FP32 Y plane when asked for: bit-exact conv mode / plane getters)
+ *
+ * = reference converImgU8toYCbCr (src/libsrcnn.cpp:233-272) followed by FRAWResizeEngine::scale in its UPSCALE order,
+ *   vertical pass then horizontal pass with an FP32 intermediate (src/frawscale.cpp:238-278, 288-385), for the plane /
+ *   filter mapping of src/libsrcnn.cpp:675-714 (plane 0 = configured filter, others bilinear or box).
+ *
+ * A CTA owns a TH x TW tile of the output.  The source footprint of the tile (from the compact contribution tables) is
+ * colour-converted once into shared memory, the vertical pass runs shared -> shared, the horizontal pass shared ->
+ * registers -> global.  The 4-byte planes of the unfused sequence (source planes, intermediate plane, FP32 Y) never
+ * reach HBM: at 1920x1080 -> 3840x2160 RGB the front end moves 6 + 66 + 17 MB instead of 6 + 25 + 25 + 50 + 50 + 100
+ * + 33 + 17 MB.
+ *
+ * Arithmetic is that of the separate kernels (resize.cu, color.cu) and therefore bit-exact against the oracle:
+ * unfused FP32 colour conversion in the reference's association order; per destination sample a double accumulator
+ * from 0.0, taps ascending, separately rounded multiply and add, one rounding to float after EACH pass.  Two
+ * identities cut the FP64 work without changing a bit: taps whose weight is exactly 0 are left out (compact tables,
+ * contrib.h), and where every weight of a table has <= 29 significant bits (bilinear at x2: 0.25 / 0.75) the product
+ * with an FP32 sample is exact, so one fused multiply-add gives the same double as multiply-then-add.  Shared memory
+ * holds the planes as doubles: the (exact) float -> double conversion is paid once per element instead of per tap.
+ */
+#include "kernels.h"
+
+#include <algorithm>
+#include <climits>
+
+namespace srcnn {
+
+namespace {
+
+constexpr int TH = 32, TW = 128, NT = 256, NW = NT / 32;
+constexpr int RPT = TH / (NT / TW);        /* destination rows per thread in the horizontal pass */
+
+struct PrepParams {
+    const uint8_t* src;         /* source row src_row0 */
+    unsigned w, src_row0;
+    unsigned ow, oh;
+    unsigned e0, e1;            /* destination rows computed */
+    float* planes; size_t plane_stride;   /* plane p row 0 = destination row e0 */
+    int write_y32;
+    __half* y16; int pitch, y16_rows; int strip_row0;
+    const int *vyl, *vcl, *hyl, *hcl;     /* compact lefts   */
+    const double *vyw, *vcw, *hyw, *hcw;  /* compact weights */
+    int SR, SC;                 /* shared-memory capacity of the source footprint (rows, columns) */
+};
+
+__device__ __forceinline__ void ycbcr_of(float r, float g, float b, float& y, float& cb, float& cr)
+{
+    /* same expression trees as color.cu (reference src/libsrcnn.cpp:245-270) */
+    y  = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+    cb = __fadd_rn(__fsub_rn(__fsub_rn(128.f, __fmul_rn(0.1687f, r)), __fmul_rn(0.3313f, g)), __fmul_rn(0.5f, b));
+    cr = __fsub_rn(__fsub_rn(__fadd_rn(128.f, __fmul_rn(0.5f, r)), __fmul_rn(0.4187f, g)), __fmul_rn(0.0813f, b));
+}
+
+/* acc + w * v the way the reference does it (two roundings), or fused when the product is known to be exact */
+template <bool FMA>
+__device__ __forceinline__ double mac(double acc, double w, double v)
+{
+    return FMA ? __fma_rn(w, v, acc) : __dadd_rn(acc, __dmul_rn(w, v));
+}
+
+/* vertical pass of one plane, shared -> shared: warp = one destination row at a time, lanes = footprint columns,
+ * three 32-column chunks in flight (independent accumulator chains hide the FP64 latency).  vl / vw: this tile's
+ * slice of the contribution table, staged in shared memory (left already relative to the footprint). */
+template <int WIN, bool FMA, int SC>
+__device__ __forceinline__ void vpass(const double* __restrict__ S, double* __restrict__ T, int nc, int ny,
+                                      const int* __restrict__ vl, const double* __restrict__ vw, int warp, int lane)
+{
+    #pragma unroll 1
+    for (int y = warp; y < ny; y += NW) {
+        double wv[WIN];
+        #pragma unroll
+        for (int i = 0; i < WIN; i++) wv[i] = vw[y * WIN + i];
+        const double* s = S + vl[y] * SC;
+        double* t = T + y * SC;
+        #pragma unroll 1
+        for (int cb = 0; cb < nc; cb += 96) {
+            const int c0 = cb + lane, c1 = c0 + 32, c2 = c0 + 64;
+            const int k0 = min(c0, nc - 1), k1 = min(c1, nc - 1), k2 = min(c2, nc - 1);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            #pragma unroll
+            for (int i = 0; i < WIN; i++) {
+                a0 = mac<FMA>(a0, wv[i], s[i * SC + k0]);
+                a1 = mac<FMA>(a1, wv[i], s[i * SC + k1]);
+                a2 = mac<FMA>(a2, wv[i], s[i * SC + k2]);
+            }
+            /* the reference's FP32 intermediate plane */
+            if (c0 < nc) t[c0] = (double)__double2float_rn(a0);
+            if (c1 < nc) t[c1] = (double)__double2float_rn(a1);
+            if (c2 < nc) t[c2] = (double)__double2float_rn(a2);
+        }
+    }
+}
+
+/* horizontal pass of one plane for this thread's column: NR rows from T (stride SC) -> f(r, value) */
+template <int WIN, bool FMA, int SC, typename F>
+__device__ __forceinline__ void hpass(const double* __restrict__ t, const double (&wv)[WIN], int nrows, F&& emit)
+{
+    if (nrows == RPT) {
+        #pragma unroll 8
+        for (int r = 0; r < RPT; r++) {
+            double acc = 0.0;
+            #pragma unroll
+            for (int i = 0; i < WIN; i++) acc = mac<FMA>(acc, wv[i], t[r * SC + i]);
+            emit(r, __double2float_rn(acc));
+        }
+    } else {
+        #pragma unroll 1
+        for (int r = 0; r < nrows; r++) {
+            double acc = 0.0;
+            #pragma unroll
+            for (int i = 0; i < WIN; i++) acc = mac<FMA>(acc, wv[i], t[r * SC + i]);
+            emit(r, __double2float_rn(acc));
+        }
+    }
+}
+
+template <int D, int WY, int WC, bool CFMA, int SC>
+__global__ void __launch_bounds__(NT)
+prep_kernel(const PrepParams p)
+{
+    extern __shared__ double sm[];
+    double* S = sm;                                   /* [D][SR][SC]  colour-converted source footprint */
+    double* T = sm + D * p.SR * SC;                   /* [TH][SC]     one plane after the vertical pass */
+    __shared__ int s_lim[4];
+    __shared__ int s_vl[2][TH];                       /* this tile's rows of the vertical tables */
+    __shared__ double s_vwy[TH * WY], s_vwc[TH * WC];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned x0 = blockIdx.x * TW, gy0 = p.e0 + blockIdx.y * TH;
+    const int ny = (int)min((unsigned)TH, p.e1 - gy0), nx = (int)min((unsigned)TW, p.ow - x0);
+    const int SR = p.SR;
+
+    /* this thread's column of the horizontal tables (global loads overlap the footprint set-up) */
+    const int x = tid & (TW - 1), rbeg = (tid / TW) * RPT;
+    const unsigned gx = x0 + x;
+    const bool col_ok = x < nx;
+    double wy[WY], wc[WC];
+    int hly = 0, hlc = 0;
+    if (col_ok) {
+        hly = __ldg(p.hyl + gx); hlc = __ldg(p.hcl + gx);
+        #pragma unroll
+        for (int i = 0; i < WY; i++) wy[i] = __ldg(p.hyw + gx * WY + i);
+        #pragma unroll
+        for (int i = 0; i < WC; i++) wc[i] = __ldg(p.hcw + gx * WC + i);
+    }
+
+    if (tid == 0) { s_lim[0] = INT_MAX; s_lim[1] = -1; s_lim[2] = INT_MAX; s_lim[3] = -1; }
+    __syncthreads();
+    if (tid < ny) {
+        const int a = __ldg(p.vyl + gy0 + tid), b = __ldg(p.vcl + gy0 + tid);
+        s_vl[0][tid] = a; s_vl[1][tid] = b;
+        atomicMin(&s_lim[0], min(a, b)); atomicMax(&s_lim[1], max(a + WY, b + WC));
+    }
+    if (tid >= TH && tid < TH + nx) {                 /* (a different warp than the row entries above) */
+        const int a = __ldg(p.hyl + x0 + tid - TH), b = __ldg(p.hcl + x0 + tid - TH);
+        atomicMin(&s_lim[2], min(a, b)); atomicMax(&s_lim[3], max(a + WY, b + WC));
+    }
+    for (int i = tid; i < ny * WY; i += NT) s_vwy[i] = __ldg(p.vyw + gy0 * WY + i);
+    for (int i = tid; i < ny * WC; i += NT) s_vwc[i] = __ldg(p.vcw + gy0 * WC + i);
+    __syncthreads();
+    const int rlo = s_lim[0], nr = s_lim[1] - rlo, clo = s_lim[2], nc = s_lim[3] - clo;
+    if (tid < ny) { s_vl[0][tid] -= rlo; s_vl[1][tid] -= rlo; }      /* made visible by the barrier after colour-in */
+
+    /* 1. colour-in of the footprint: warp = source row, lanes = source columns, three chunks in flight */
+    {
+        const int pl = SR * SC;
+        #pragma unroll 1
+        for (int r = warp; r < nr; r += NW) {
+            const uint8_t* row = p.src + ((size_t)(rlo + r - (int)p.src_row0) * p.w + (size_t)clo) * D;
+            double* s = S + r * SC;
+            #pragma unroll 1
+            for (int cb = 0; cb < nc; cb += 96) {
+                uint32_t v[3][D];
+                #pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const uint8_t* px = row + min(cb + lane + 32 * k, nc - 1) * D;
+                    #pragma unroll
+                    for (int j = 0; j < D; j++) v[k][j] = __ldg(px + j);
+                }
+                #pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int c = cb + lane + 32 * k;
+                    float y, cb_, cr;
+                    ycbcr_of((float)v[k][0], (float)v[k][1], (float)v[k][2], y, cb_, cr);
+                    if (c < nc) {
+                        s[c] = (double)y; s[pl + c] = (double)cb_; s[2 * pl + c] = (double)cr;
+                        if (D == 4) s[3 * pl + c] = (double)(float)v[k][D - 1];
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int nrows = max(0, min(ny - rbeg, RPT));
+    const int ybase = (int)gy0 - p.strip_row0 + kHaloRows;       /* conv-input plane row of tile row 0 */
+
+    /* 2. plane 0 (Y): configured filter */
+    vpass<WY, false, SC>(S, T, nc, ny, s_vl[0], s_vwy, warp, lane);
+    __syncthreads();
+    if (col_ok) {
+        const double* t = T + rbeg * SC + (hly - clo);
+        float* o32 = p.planes + (size_t)(gy0 + rbeg - p.e0) * p.ow + gx;
+        /* conv input: FP16 (RN), plane column = image column + 8 */
+        __half* o16 = p.y16 ? p.y16 + (size_t)(ybase + rbeg) * p.pitch + gx + kY16PadL : nullptr;
+        const unsigned ow = p.ow; const int pitch = p.pitch;
+        if (o16 && !p.write_y32)
+            hpass<WY, false, SC>(t, wy, nrows, [&](int r, float v) { o16[r * pitch] = __float2half_rn(v); });
+        else
+            hpass<WY, false, SC>(t, wy, nrows, [&](int r, float v) {
+                if (p.write_y32) o32[(size_t)r * ow] = v;
+                if (o16) o16[r * pitch] = __float2half_rn(v);
+            });
+    }
+    __syncthreads();            /* the tile's conv-input values are visible to the whole CTA; T is free again */
+
+    /* 2b. replicate padding of the conv-input plane around the image (only border tiles do any work):
+     * columns 0..7 repeat image column 0, columns ow+8..pitch-1 repeat column ow-1, the rows above / below the image
+     * repeat row 0 / oh-1 -- conv I clamps Y coordinates (src/libsrcnn.cpp:362-392) */
+    if (p.y16) {
+        const bool first_col = (x0 == 0), last_col = (x0 + nx == p.ow);
+        if (first_col || last_col) {
+            const int c_hi = (int)p.ow + kY16PadL, npad_r = last_col ? p.pitch - c_hi : 0, npad_l = first_col ? kY16PadL : 0;
+            const int per_row = npad_l + npad_r;
+            for (int idx = tid; idx < ny * per_row; idx += NT) {
+                const int r = idx / per_row, k = idx - r * per_row;
+                __half* row = p.y16 + (size_t)(ybase + r) * p.pitch;
+                if (k < npad_l) row[k] = row[kY16PadL];
+                else            row[c_hi + (k - npad_l)] = row[c_hi - 1];
+            }
+            __syncthreads();
+        }
+        const bool top = (gy0 == 0) && ybase > 0, bottom = (gy0 + ny == p.oh) && (ybase + ny < p.y16_rows);
+        if (top || bottom) {
+            /* this tile's column span of the plane, pads included */
+            const int ca = first_col ? 0 : (int)x0 + kY16PadL, cb = last_col ? p.pitch : (int)x0 + nx + kY16PadL;
+            const int span = cb - ca;
+            if (top) {
+                const __half* from = p.y16 + (size_t)ybase * p.pitch + ca;
+                for (int idx = tid; idx < ybase * span; idx += NT) {
+                    const int r = idx / span, c = idx - r * span;
+                    p.y16[(size_t)r * p.pitch + ca + c] = from[c];
+                }
+            }
+            if (bottom) {
+                const int rb = ybase + ny, nrep = p.y16_rows - rb;
+                const __half* from = p.y16 + (size_t)(rb - 1) * p.pitch + ca;
+                for (int idx = tid; idx < nrep * span; idx += NT) {
+                    const int r = idx / span, c = idx - r * span;
+                    p.y16[(size_t)(rb + r) * p.pitch + ca + c] = from[c];
+                }
+            }
+        }
+    }
+
+    /* 3. planes 1 .. D-1 (Cb, Cr, A): bilinear / box tables */
+    const double* tc = T + rbeg * SC + (hlc - clo);
+    #pragma unroll 1
+    for (int pl = 1; pl < D; pl++) {
+        vpass<WC, CFMA, SC>(S + pl * SR * SC, T, nc, ny, s_vl[1], s_vwc, warp, lane);
+        __syncthreads();
+        if (col_ok) {
+            float* out = p.planes + pl * p.plane_stride + (size_t)(gy0 + rbeg - p.e0) * p.ow + gx;
+            const unsigned ow = p.ow;
+            hpass<WC, CFMA, SC>(tc, wc, nrows, [&](int r, float v) { out[(size_t)r * ow] = v; });
+        }
+        __syncthreads();
+    }
+}
+
+template <int D, int WY, int WC, bool CFMA, int SC>
+int launch_one(const PrepParams& p, dim3 grid, cudaStream_t s)
+{
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(prep_kernel<D, WY, WC, CFMA, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+            cudaGetLastError(); return 0;
+        }
+        configured = true;
+    }
+    const size_t smem = ((size_t)D * p.SR + TH) * SC * sizeof(double);
+    prep_kernel<D, WY, WC, CFMA, SC><<<grid, NT, smem, s>>>(p);
+    return 1;
+}
+
+/* shared-memory row pitch (doubles): 72 covers magnifications >= 2 (128/2 + window), 104 those >= 1.5 */
+template <int D, int WY, bool CFMA>
+int launch_sc(const PrepParams& p, dim3 grid, cudaStream_t s)
+{
+    if (p.SC <= 72)  return launch_one<D, WY, 2, CFMA, 72>(p, grid, s);
+    if (p.SC <= 104) return launch_one<D, WY, 2, CFMA, 104>(p, grid, s);
+    return 0;                                        /* shallower magnification: the separate kernels */
+}
+
+template <int D>
+int launch_d(const PrepParams& p, int wy, bool cfma, dim3 grid, cudaStream_t s)
+{
+    switch (wy) {
+        case 2:  return cfma ? launch_sc<D, 2, true>(p, grid, s) : launch_sc<D, 2, false>(p, grid, s);
+        case 4:  return cfma ? launch_sc<D, 4, true>(p, grid, s) : launch_sc<D, 4, false>(p, grid, s);
+        default: return cfma ? launch_sc<D, 6, true>(p, grid, s) : launch_sc<D, 6, false>(p, grid, s);
+    }
+}
+
+/* largest source footprint (extent along one axis) of any tile of `tile` destination samples starting at d0 */
+int max_footprint(const int* ly, int wy, const int* lc, int wc, unsigned d0, unsigned d1, unsigned tile)
+{
+    int best = 0;
+    for (unsigned a = d0; a < d1; a += tile) {
+        const unsigned b = std::min(d1, a + tile);
+        int lo = INT_MAX, hi = -1;
+        for (unsigned u = a; u < b; u++) {
+            lo = std::min(lo, std::min(ly[u], lc[u]));
+            hi = std::max(hi, std::max(ly[u] + wy, lc[u] + wc));
+        }
+        best = std::max(best, hi - lo);
+    }
+    return best;
+}
+
+} // namespace
+
+bool prep_supported(const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc)
+{
+    if (!vy.cleft || !vc.cleft || !hy.cleft || !hc.cleft) return false;
+    if (vy.cwin != hy.cwin || (vy.cwin != 2 && vy.cwin != 4 && vy.cwin != 6)) return false;
+    return vc.cwin == 2 && hc.cwin == 2;
+}
+
+int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, unsigned ow, unsigned oh,
+                unsigned e0, unsigned e1, float* planes, size_t plane_stride, bool write_y32,
+                __half* y16, Y16Geom g, unsigned strip_row0,
+                const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc,
+                const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, cudaStream_t s)
+{
+    if (!prep_supported(vy, vc, hy, hc) || (d != 3 && d != 4)) return 0;
+    PrepParams p;
+    p.src = src; p.w = w; p.src_row0 = src_row0; p.ow = ow; p.oh = oh; p.e0 = e0; p.e1 = e1;
+    p.planes = planes; p.plane_stride = plane_stride; p.write_y32 = write_y32 ? 1 : 0;
+    p.y16 = y16; p.pitch = g.pitch; p.y16_rows = g.rows; p.strip_row0 = (int)strip_row0;
+    p.vyl = vy.cleft; p.vcl = vc.cleft; p.hyl = hy.cleft; p.hcl = hc.cleft;
+    p.vyw = vy.cw; p.vcw = vc.cw; p.hyw = hy.cw; p.hcw = hc.cw;
+    p.SR = max_footprint(h_vyl, vy.cwin, h_vcl, vc.cwin, e0, e1, TH);
+    p.SC = max_footprint(h_hyl, hy.cwin, h_hcl, hc.cwin, 0, ow, TW);
+    if (((size_t)d * p.SR + TH) * 104 * sizeof(double) > 160 * 1024) return 0;
+    if ((size_t)oh * 8 >= (size_t)INT_MAX || (size_t)ow * 8 >= (size_t)INT_MAX) return 0;
+    dim3 grid((ow + TW - 1) / TW, (e1 - e0 + TH - 1) / TH);
+    if (grid.y > 65535u) return 0;
+    const bool cfma = vc.exact29 && hc.exact29;
+    return d == 3 ? launch_d<3>(p, vy.cwin, cfma, grid, s) : launch_d<4>(p, vy.cwin, cfma, grid, s);
+}
+
+} // namespace srcnn

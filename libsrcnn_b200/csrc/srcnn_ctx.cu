@@ -147,6 +147,9 @@ struct srcnn_b200_ctx {
     bool stage_pageable = true;               /* pageable results go through pinned staging (SRCNN_B200_STAGE=0: off) */
     std::vector<cudaEvent_t> pipe_ev;         /* 3 per sub-strip: uploaded, computed, downloaded                      */
     HostCopier copier;
+    bool fuse_front = true;                   /* one-kernel front end (SRCNN_B200_FUSE=0: the separate kernels)       */
+    bool keep_planes = false;                 /* also write the FP32 interpolated Y plane in tensor mode (getters)    */
+    bool last_has_y32 = false;
     /* last pass, for the plane getters */
     Plan last{}; bool have_last = false; size_t last_plane_stride = 0;
 };
@@ -187,31 +190,41 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     if (it != ctx->tables.end()) { *out = it->second; return 0; }
     TableDev* t = new TableDev;
     build_axis_table(filter, dst, src, t->host);
+    /* device image: int arrays left | count | dleft | cleft, then double arrays w | dw | cw */
+    const AxisTable& h = t->host;
     const size_t ints = (size_t)dst * sizeof(int);
-    const size_t nints = t->host.dense ? 3 : 2;
-    const size_t ints_al = (nints * ints + 15) / 16 * 16;
-    const size_t wbytes = t->host.w.size() * sizeof(double);
-    const size_t bytes = ints_al + wbytes * (t->host.dense ? 2 : 1);
+    const size_t ints_al = (4 * ints + 15) / 16 * 16;
+    const size_t wbytes = h.w.size() * sizeof(double), cbytes = h.cw.size() * sizeof(double);
+    const size_t bytes = ints_al + 2 * wbytes + cbytes;
     std::vector<unsigned char> img(bytes, 0);
     int* L = reinterpret_cast<int*>(img.data());
     int* C = L + dst;
-    for (unsigned u = 0; u < dst; u++) { L[u] = t->host.left[u]; C[u] = t->host.right[u] - t->host.left[u] + 1; }
-    memcpy(img.data() + ints_al, t->host.w.data(), wbytes);
-    if (t->host.dense) {
-        memcpy(C + dst, t->host.dleft.data(), ints);
-        memcpy(img.data() + ints_al + wbytes, t->host.dw.data(), wbytes);
+    for (unsigned u = 0; u < dst; u++) { L[u] = h.left[u]; C[u] = h.right[u] - h.left[u] + 1; }
+    memcpy(img.data() + ints_al, h.w.data(), wbytes);
+    if (h.dense) {
+        memcpy(C + dst, h.dleft.data(), ints);
+        memcpy(img.data() + ints_al + wbytes, h.dw.data(), wbytes);
+    }
+    if (h.compact) {
+        memcpy(C + 2 * dst, h.cleft.data(), ints);
+        memcpy(img.data() + ints_al + 2 * wbytes, h.cw.data(), cbytes);
     }
     cudaError_t e = cudaMalloc(&t->dev, bytes);
     if (e != cudaSuccess) { delete t; return fail_cuda(ctx, e, "cudaMalloc(table)"); }
     e = cudaMemcpyAsync(t->dev, img.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);      /* img is a temporary */
     if (e != cudaSuccess) { cudaFree(t->dev); delete t; return fail_cuda(ctx, e, "upload(table)"); }
-    t->view.left  = reinterpret_cast<const int*>(t->dev);
+    const unsigned char* base = static_cast<unsigned char*>(t->dev);
+    t->view.left  = reinterpret_cast<const int*>(base);
     t->view.count = t->view.left + dst;
-    t->view.w     = reinterpret_cast<const double*>(static_cast<unsigned char*>(t->dev) + ints_al);
-    t->view.win   = t->host.win;
-    t->view.dleft = t->host.dense ? t->view.count + dst : nullptr;
-    t->view.dw    = t->host.dense ? t->view.w + t->host.w.size() : nullptr;
+    t->view.w     = reinterpret_cast<const double*>(base + ints_al);
+    t->view.win   = h.win;
+    t->view.dleft = h.dense ? t->view.left + 2 * dst : nullptr;
+    t->view.dw    = h.dense ? reinterpret_cast<const double*>(base + ints_al + wbytes) : nullptr;
+    t->view.cleft = h.compact ? t->view.left + 3 * dst : nullptr;
+    t->view.cw    = h.compact ? reinterpret_cast<const double*>(base + ints_al + 2 * wbytes) : nullptr;
+    t->view.cwin  = h.cwin;
+    t->view.exact29 = h.exact29 ? 1 : 0;
     ctx->tables[key] = t;
     *out = t;
     return 0;
@@ -225,6 +238,7 @@ void source_rows(const AxisTable& a, const AxisTable& b, unsigned e0, unsigned e
         for (unsigned r = e0; r < e1; r++) {
             lo = std::min(lo, t->left[r]); hi = std::max(hi, t->right[r]);
             if (t->dense) { lo = std::min(lo, t->dleft[r]); hi = std::max(hi, t->dleft[r] + t->win - 1); }
+            if (t->compact) { lo = std::min(lo, t->cleft[r]); hi = std::max(hi, t->cleft[r] + t->cwin - 1); }
         }
     s0 = (unsigned)lo; s1 = (unsigned)hi + 1;
 }
@@ -278,58 +292,74 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
     auto al = [](size_t n) { return (n + 63) / 64 * 64; };
     const size_t ps_src = al((size_t)srows * p.w), ps_dst = al((size_t)erows * p.ow);
     const size_t ps_tmp = al(p.hfirst ? (size_t)srows * p.ow : (size_t)erows * p.w);
-    CK(ctx->planes_src.ensure(ps_src * p.d * sizeof(float)));
+    const bool tensor = ctx->conv_mode == SRCNN_B200_CONV_TENSOR;
     CK(ctx->planes_dst.ensure(ps_dst * p.d * sizeof(float)));
-    if (p.need_h && p.need_v) CK(ctx->tmp.ensure(ps_tmp * p.d * sizeof(float)));
     CK(ctx->yprime.ensure((size_t)orows * p.ow * sizeof(float)));
-    float* P_src = static_cast<float*>(ctx->planes_src.p);
     float* P_dst = static_cast<float*>(ctx->planes_dst.p);
-    float* P_tmp = static_cast<float*>(ctx->tmp.p);
     float* Yp    = static_cast<float*>(ctx->yprime.p);
+    const Y16Geom g = y16_geometry(p.ow, orows);
+    if (tensor) CK(ctx->y16.ensure((size_t)g.pitch * g.rows * sizeof(__half)));
     cudaStream_t s = ctx->stream;
 
     Stamp st(ctx);
-    /* 1. colour-in on the source rows the strip needs */
-    launch_color_in(d_src, (size_t)srows * p.w, p.d, P_src, ps_src, s); ctx->launches++;
-    st.mark();
-    /* 2./3. separable resize; order as in FRAWResizeEngine::scale (src/frawscale.cpp:195-278) */
-    const AxisTableDev none{};
-    if (!p.need_h && !p.need_v) {
-        /* equal size: plain copy of every plane (the reference copies only half of it, a bug we do not keep) */
-        for (unsigned pl = 0; pl < p.d; pl++)
-            CK(cudaMemcpyAsync(P_dst + pl * ps_dst, P_src + pl * ps_src, (size_t)erows * p.ow * sizeof(float),
-                               cudaMemcpyDeviceToDevice, s));
-        st.mark(); st.mark();
-    } else if (p.hfirst) {
-        if (p.need_h) {
-            float* o = p.need_v ? P_tmp : P_dst; const size_t os = p.need_v ? ps_tmp : ps_dst;
-            launch_resize_horizontal(P_src, ps_src, p.w, o, os, p.ow, srows, p.d, hy->view, hc->view, s); ctx->launches++;
-        }
-        st.mark();
-        if (p.need_v) {
-            const float* i = p.need_h ? P_tmp : P_src; const size_t is = p.need_h ? ps_tmp : ps_src;
-            launch_resize_vertical(i, is, p.ow, p.s0, P_dst, ps_dst, p.e0, erows, p.d, vy->view, vc->view, s); ctx->launches++;
-        }
-        st.mark();
+    /* 1.-4. front end.  Preferred: ONE kernel (colour-in + both resampling passes + conv-input pack, prep.cu) */
+    const bool y32 = !tensor || ctx->keep_planes;
+    bool fused = false;
+    if (ctx->fuse_front && !p.hfirst && p.need_h && p.need_v && prep_supported(vy->view, vc->view, hy->view, hc->view)) {
+        fused = launch_prep(d_src, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, P_dst, ps_dst, y32,
+                            tensor ? static_cast<__half*>(ctx->y16.p) : nullptr, g, p.r0,
+                            vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
+                            hy->host.cleft.data(), hc->host.cleft.data(), s) != 0;
+    }
+    if (fused) {
+        ctx->launches++;
+        st.mark(); st.mark(); st.mark(); st.mark();
+        ctx->last_has_y32 = y32;
     } else {
-        if (p.need_v) {
-            float* o = p.need_h ? P_tmp : P_dst; const size_t os = p.need_h ? ps_tmp : ps_dst;
-            launch_resize_vertical(P_src, ps_src, p.w, p.s0, o, os, p.e0, erows, p.d, vy->view, vc->view, s); ctx->launches++;
-        }
+        CK(ctx->planes_src.ensure(ps_src * p.d * sizeof(float)));
+        if (p.need_h && p.need_v) CK(ctx->tmp.ensure(ps_tmp * p.d * sizeof(float)));
+        float* P_src = static_cast<float*>(ctx->planes_src.p);
+        float* P_tmp = static_cast<float*>(ctx->tmp.p);
+        ctx->last_has_y32 = true;
+        /* 1. colour-in on the source rows the strip needs */
+        launch_color_in(d_src, (size_t)srows * p.w, p.d, P_src, ps_src, s); ctx->launches++;
         st.mark();
-        if (p.need_h) {
-            const float* i = p.need_v ? P_tmp : P_src; const size_t is = p.need_v ? ps_tmp : ps_src;
-            launch_resize_horizontal(i, is, p.w, P_dst, ps_dst, p.ow, erows, p.d, hy->view, hc->view, s); ctx->launches++;
+        /* 2./3. separable resize; order as in FRAWResizeEngine::scale (src/frawscale.cpp:195-278) */
+        if (!p.need_h && !p.need_v) {
+            /* equal size: plain copy of every plane (the reference copies only half of it, a bug we do not keep) */
+            for (unsigned pl = 0; pl < p.d; pl++)
+                CK(cudaMemcpyAsync(P_dst + pl * ps_dst, P_src + pl * ps_src, (size_t)erows * p.ow * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+            st.mark(); st.mark();
+        } else if (p.hfirst) {
+            if (p.need_h) {
+                float* o = p.need_v ? P_tmp : P_dst; const size_t os = p.need_v ? ps_tmp : ps_dst;
+                launch_resize_horizontal(P_src, ps_src, p.w, o, os, p.ow, srows, p.d, hy->view, hc->view, s); ctx->launches += 2;
+            }
+            st.mark();
+            if (p.need_v) {
+                const float* i = p.need_h ? P_tmp : P_src; const size_t is = p.need_h ? ps_tmp : ps_src;
+                launch_resize_vertical(i, is, p.ow, p.s0, P_dst, ps_dst, p.e0, erows, p.d, vy->view, vc->view, s); ctx->launches += 2;
+            }
+            st.mark();
+        } else {
+            if (p.need_v) {
+                float* o = p.need_h ? P_tmp : P_dst; const size_t os = p.need_h ? ps_tmp : ps_dst;
+                launch_resize_vertical(P_src, ps_src, p.w, p.s0, o, os, p.e0, erows, p.d, vy->view, vc->view, s); ctx->launches += 2;
+            }
+            st.mark();
+            if (p.need_h) {
+                const float* i = p.need_v ? P_tmp : P_src; const size_t is = p.need_v ? ps_tmp : ps_src;
+                launch_resize_horizontal(i, is, p.w, P_dst, ps_dst, p.ow, erows, p.d, hy->view, hc->view, s); ctx->launches += 2;
+            }
+            st.mark();
         }
+        /* 4. conv-input pack */
+        if (tensor) { launch_pack_y16(P_dst, p.ow, p.oh, p.e0, static_cast<__half*>(ctx->y16.p), g, p.r0, s); ctx->launches++; }
         st.mark();
     }
-    (void)none;
-    /* 4./5. fused conv I+II+III on the Y plane */
-    if (ctx->conv_mode == SRCNN_B200_CONV_TENSOR) {
-        const Y16Geom g = y16_geometry(p.ow, orows);
-        CK(ctx->y16.ensure((size_t)g.pitch * g.rows * sizeof(__half)));
-        launch_pack_y16(P_dst, p.ow, p.oh, p.e0, static_cast<__half*>(ctx->y16.p), g, p.r0, s); ctx->launches++;
-        st.mark();
+    /* 5. fused conv I+II+III on the Y plane */
+    if (tensor) {
         if (launch_conv_tc(ctx->tc, static_cast<const __half*>(ctx->y16.p), g, p.ow, p.oh, Yp, p.r0, p.r1,
                            ctx->num_sms, s)) {
             ctx->err = std::string("conv_tc: ") + conv_tc_error(ctx->tc);
@@ -337,7 +367,6 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
         }
         ctx->launches++;
     } else {
-        st.mark();
         launch_conv_exact(P_dst, p.ow, p.oh, p.e0, erows, Yp, p.r0, p.r1, s); ctx->launches++;
     }
     st.mark();
@@ -398,6 +427,7 @@ int srcnn_b200_create(int device, srcnn_b200_ctx** out)
     if (const char* e = getenv("SRCNN_B200_CHAIN")) ctx->chain_tensor = (strcmp(e, "tensor") == 0);
     if (const char* e = getenv("SRCNN_B200_STRIP_MB")) { const double mb = atof(e); if (mb >= 0.25) ctx->strip_bytes = (size_t)(mb * 1048576.0); }
     if (const char* e = getenv("SRCNN_B200_STAGE")) ctx->stage_pageable = atoi(e) != 0;
+    if (const char* e = getenv("SRCNN_B200_FUSE")) ctx->fuse_front = atoi(e) != 0;
     {
         unsigned nt = std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2));
         if (const char* e = getenv("SRCNN_B200_COPY_THREADS")) nt = (unsigned)std::max(1, atoi(e));
@@ -742,6 +772,7 @@ int srcnn_b200_get_plane(srcnn_b200_ctx* ctx, int which, float* host, size_t cap
     if (!ctx || !ctx->have_last || !host || which < 0 || which > 4) return SRCNN_B200_EINVAL;
     const Plan& p = ctx->last;
     if (which == 3 && p.d != 4) return SRCNN_B200_EINVAL;
+    if (which == 0 && !ctx->last_has_y32) return SRCNN_B200_EINVAL;      /* see srcnn_b200_set_keep_planes */
     const float* srcp; unsigned r0, nr;
     if (which == 4) { srcp = static_cast<const float*>(ctx->yprime.p); r0 = p.r0; nr = p.r1 - p.r0; }
     else { srcp = static_cast<const float*>(ctx->planes_dst.p) + (size_t)which * ctx->last_plane_stride; r0 = p.e0; nr = p.e1 - p.e0; }
@@ -754,6 +785,7 @@ int srcnn_b200_get_plane(srcnn_b200_ctx* ctx, int which, float* host, size_t cap
     return 0;
 }
 
+int srcnn_b200_set_keep_planes(srcnn_b200_ctx* ctx, int on) { if (!ctx) return SRCNN_B200_EINVAL; ctx->keep_planes = on != 0; return 0; }
 int srcnn_b200_set_timing(srcnn_b200_ctx* ctx, int on) { if (!ctx) return SRCNN_B200_EINVAL; ctx->timing = on != 0; return 0; }
 int srcnn_b200_last_timings(srcnn_b200_ctx* ctx, float* ms7)
 {
@@ -872,6 +904,22 @@ int srcnn_b200_contrib_table(int filter, unsigned dst, unsigned src, int* left, 
         for (int i = 0; i < maxwin; i++) weights[(size_t)u * maxwin + i] = i < t.win ? t.w[(size_t)u * t.win + i] : 0.0;
     }
     return t.win;
+}
+
+int srcnn_b200_contrib_table_compact(int filter, unsigned dst, unsigned src, int* cleft, double* weights, int maxwin,
+                                     int* exact29)
+{
+    if (!dst || !src || !cleft || !weights) return SRCNN_B200_EINVAL;
+    const int f = (filter >= kNearest && filter <= kBspline) ? filter : kNearest;
+    AxisTable t; build_axis_table(f, dst, src, t);
+    if (!t.compact) return 0;
+    if (t.cwin > maxwin) return -1;
+    for (unsigned u = 0; u < dst; u++) {
+        cleft[u] = t.cleft[u];
+        for (int i = 0; i < maxwin; i++) weights[(size_t)u * maxwin + i] = i < t.cwin ? t.cw[(size_t)u * t.cwin + i] : 0.0;
+    }
+    if (exact29) *exact29 = t.exact29 ? 1 : 0;
+    return t.cwin;
 }
 
 } // extern "C"

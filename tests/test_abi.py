@@ -72,6 +72,29 @@ def test_contrib_table_matches_oracle(filt, dst, src):
     assert np.array_equal(La, Lb) and np.array_equal(Ra, Rb) and np.array_equal(Wa, Wb)
 
 
+@pytest.mark.parametrize("filt", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("dst,src", [(512, 256), (3840, 1920), (97, 64), (1024, 512), (300, 299), (8, 3), (5760, 3840), (1024, 256)])
+def test_compact_table_is_the_reference_table_minus_exact_zeros(filt, dst, src):
+    """the table the fused front-end kernel reads: same weights at the same source indices as the oracle's table,
+    only taps whose weight is exactly 0.0 are missing (they add +-0 to the double accumulator: no effect)"""
+    cwin, cl, cw, exact29 = S.contrib_table_compact(filt, dst, src)
+    Lb, Rb, Wb = O.best().table(filt, dst, src)
+    if cwin == 0:
+        assert src < 8
+        return
+    assert cwin % 2 == 0 and cwin <= Wb.shape[1]
+    assert (cl >= 0).all() and (cl + cwin <= src).all()
+    for u in range(dst):
+        full = np.zeros(src); full[Lb[u]:Rb[u] + 1] = Wb[u, :Rb[u] - Lb[u] + 1]
+        comp = np.zeros(src); comp[cl[u]:cl[u] + cwin] = cw[u, :cwin]
+        assert np.array_equal(full, comp)
+    # <= 29 significant bits <=> the low 24 mantissa bits of every weight are clear
+    bits = cw[:, :cwin].copy().view(np.uint64)
+    assert exact29 == bool(((bits & np.uint64((1 << 24) - 1)) == 0).all())
+    if filt == S.BILINEAR and dst == 2 * src:
+        assert exact29          # 0.25 / 0.75: the fused multiply-add shortcut applies to the chroma planes at x2
+
+
 def test_argument_validation_needs_no_gpu():
     img = O.synth("uniform", 8, 8, 3, 0)
     assert S.process_srcnn(img, 0.0)[0] == -2
