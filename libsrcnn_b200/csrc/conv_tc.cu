@@ -43,28 +43,36 @@ namespace srcnn {
 
 namespace {
 
-constexpr int K1 = 96, N1 = 64;     /* conv I   GEMM */
-constexpr int K2 = 64, N2 = 32;     /* conv II  GEMM (+ one K=16 step against a constant-1 operand that adds the bias) */
-constexpr int K3 = 32, N3 = 32;     /* conv III GEMM (taps as N) */
-constexpr int B1_BYTES = N1 * K1 * 2, B2_BYTES = N2 * K2 * 2, B3_BYTES = N3 * K3 * 2, B2B_BYTES = N2 * 16 * 2;
-constexpr int WIMG_BYTES = B1_BYTES + B2_BYTES + B3_BYTES + B2B_BYTES;
+constexpr int K1 = 96, N1 = 64, NROT = 9;  /* conv I   GEMM; NROT rotated weight images (the A1 window is a ring of 9 row slots) */
+constexpr int K2 = 64, N2 = 32;            /* conv II  GEMM (+ one K=16 step against a constant-1 operand that adds the bias) */
+constexpr int N3 = 16, KS3 = 12;           /* conv III GEMM per PAIR of output rows: K = 6 rows x 32 ch = 12 K-steps, N = 2 rows x 5 dx */
+constexpr int B1_BYTES = N1 * K1 * 2, B2_BYTES = N2 * K2 * 2, B2B_BYTES = N2 * 16 * 2, B3_TILE = N3 * 16 * 2;
+constexpr int B3_BYTES = KS3 * B3_TILE;
+constexpr int W_B2 = NROT * B1_BYTES, W_B2B = W_B2 + B2_BYTES, W_B3 = W_B2B + B2B_BYTES;
+constexpr int WIMG_BYTES = W_B3 + B3_BYTES;
 
-/* TMEM columns (512 allocated); every region double-buffered: index b = row & 1 */
-constexpr uint32_t D1_COL = 0, D2_COL = 128, D3_COL = 192, A1_COL = 256, A2_COL = 352, A3_COL = 416, AC_COL = 448;
-constexpr uint32_t D1_STR = 64, D2_STR = 32, D3_STR = 32, A1_STR = 48, A2_STR = 32, A3_STR = 16;
+/* TMEM columns (512 allocated).  D1/D2/A1/A2 are double-buffered by row parity, A3 is a ring of 8 conv II rows
+ * (4 pair slots), D3 is single-buffered (one set per two output rows). */
+constexpr uint32_t D1_COL = 0, D2_COL = 128, A2_COL = 192, A1_COL = 256, A3_COL = 352, D3_COL = 480, AC_COL = 496;
+constexpr uint32_t D1_STR = 64, D2_STR = 32, A1_STR = 48, A2_STR = 32, A3_SLOT = 16;
 
 /* Y16 staging ring */
 constexpr int CH_ROWS = 8, BOX_W = 144, NST = 4;
 constexpr int CH_BYTES = CH_ROWS * BOX_W * 2;
 
-/* warp roles: one control warpgroup + four 4-warp groups (TMEM lane quarter = warp & 3) */
-constexpr int W_TMA = 0, W_MMA1 = 1, W_MMA2 = 2, W_MMA3 = 3, W_IM2COL = 4, W_E1 = 8, W_E2 = 12, W_E3 = 16, NWARPS = 20;
+/* warp roles: one control warpgroup + five 4-warp groups (TMEM lane quarter = warp & 3) */
+constexpr int W_TMA = 0, W_MMA1 = 1, W_MMA2 = 2, W_MMA3 = 3, W_IM2COL = 4, W_E1 = 8, W_E2 = 16, W_E3 = 20, NWARPS = 24;
 
 /* barrier indices.  M?_DONE[b] fires when the MMAs of layer ? for a row with parity b have completed: it both frees the
  * A operand region for the producer group and publishes the accumulator to the consumer group. */
 enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + 2, D1_EMPTY = M1_DONE + 2,
        A2_FULL = D1_EMPTY + 2, M2_DONE = A2_FULL + 2, D2_EMPTY = M2_DONE + 2,
-       A3_FULL = D2_EMPTY + 2, M3_DONE = A3_FULL + 2, D3_EMPTY = M3_DONE + 2, NBAR = D3_EMPTY + 2 };
+       A3_FULL = D2_EMPTY + 2, A3_EMPTY = A3_FULL + 4, M3_DONE = A3_EMPTY + 4, D3_EMPTY = M3_DONE + 1, NBAR = D3_EMPTY + 1 };
+
+/* dynamic shared memory layout (offsets from a 1024-byte aligned base) */
+constexpr int S_Y = 0, S_W = NST * CH_BYTES, S_P = S_W + WIMG_BYTES, S_BAR = S_P + 2 * 10 * 128 * 4, S_TMEM = S_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = S_TMEM + 16 + 1024;
+static_assert(S_W % 128 == 0 && S_P % 16 == 0 && S_BAR % 8 == 0, "smem layout");
 
 __constant__ float cBias3;
 
@@ -142,6 +150,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* r)
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(addr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(addr) : "memory");
+}
 /* two FP32 -> packed FP16x2 with ReLU in one instruction; `lo` lands in the low half (even K index) */
 __device__ __forceinline__ uint32_t cvt_relu_h2(uint32_t lo, uint32_t hi)
 {
@@ -170,10 +185,12 @@ struct TcParams {
     float* out;                 /* rows [row0,row1) x dw */
     int row0, row1;
     int bands, seg_rows, nsegs;
-    const unsigned char* wimg;  /* B1 | B2 | B3 | B2-bias operand images */
+    const unsigned char* wimg;  /* B1 x 9 rotations | B2 | B2-bias | B3 operand images */
 };
 
-struct Unit { int band, ra, rb, nrows; };
+/* a work unit = one 128-column band x one row segment [ra, rb).  It streams the conv II rows q = ra-2 .. ra-3+nrows;
+ * nrows is even (output rows are produced in pairs; an odd segment computes one discarded extra row). */
+struct Unit { int band, ra, rb, npairs, nrows; };
 __device__ __forceinline__ Unit unit_of(const TcParams& p, int u)
 {
     Unit x;
@@ -181,7 +198,8 @@ __device__ __forceinline__ Unit unit_of(const TcParams& p, int u)
     const int seg = u / p.bands;
     x.ra = p.row0 + seg * p.seg_rows;
     x.rb = min(x.ra + p.seg_rows, p.row1);
-    x.nrows = x.rb - x.ra + 4;              /* intermediate rows q = ra-2 .. rb+1 */
+    x.npairs = (x.rb - x.ra + 1) >> 1;
+    x.nrows = 2 * x.npairs + 4;
     return x;
 }
 __device__ __forceinline__ int total_rows(const TcParams& p, int units)
@@ -194,31 +212,30 @@ __device__ __forceinline__ int total_rows(const TcParams& p, int units)
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
 {
-    __shared__ __align__(1024) unsigned char sY[NST * CH_BYTES];
-    __shared__ __align__(128) unsigned char sW[WIMG_BYTES];
-    __shared__ __align__(16) float sP[2][5][128];
-    __shared__ __align__(8) uint64_t s_bar[NBAR];
-    __shared__ uint32_t s_tmem;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* const sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t sY = sbase + S_Y, sW = sbase + S_W, bar0 = sbase + S_BAR;
+    float* const sP = reinterpret_cast<float*>(sgen + S_P);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto BAR = [&](int i) -> uint32_t { return bar0 + 8u * (uint32_t)i; };
 
     /* one-time setup: weights -> smem (generic proxy, then made visible to the async proxy), barriers, TMEM */
     for (int i = tid; i < WIMG_BYTES / 16; i += NWARPS * 32)
-        reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+        reinterpret_cast<uint4*>(sgen + S_W)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
     if (tid == 0) {
-        for (int i = 0; i < NST; i++) { mbar_init(smem_u32(&s_bar[Y_FULL + i]), 1); mbar_init(smem_u32(&s_bar[Y_EMPTY + i]), 4); }
+        for (int i = 0; i < NST; i++) { mbar_init(BAR(Y_FULL + i), 1); mbar_init(BAR(Y_EMPTY + i), 4); }
         for (int b = 0; b < 2; b++) {
-            mbar_init(smem_u32(&s_bar[A1_FULL + b]), 4); mbar_init(smem_u32(&s_bar[M1_DONE + b]), 1);
-            mbar_init(smem_u32(&s_bar[D1_EMPTY + b]), 4);
-            mbar_init(smem_u32(&s_bar[A2_FULL + b]), 4); mbar_init(smem_u32(&s_bar[M2_DONE + b]), 1);
-            mbar_init(smem_u32(&s_bar[D2_EMPTY + b]), 4);
-            mbar_init(smem_u32(&s_bar[A3_FULL + b]), 4); mbar_init(smem_u32(&s_bar[M3_DONE + b]), 1);
-            mbar_init(smem_u32(&s_bar[D3_EMPTY + b]), 4);
+            mbar_init(BAR(A1_FULL + b), 4); mbar_init(BAR(M1_DONE + b), 1); mbar_init(BAR(D1_EMPTY + b), 4);
+            mbar_init(BAR(A2_FULL + b), 4); mbar_init(BAR(M2_DONE + b), 1); mbar_init(BAR(D2_EMPTY + b), 4);
         }
+        for (int j = 0; j < 4; j++) { mbar_init(BAR(A3_FULL + j), 4); mbar_init(BAR(A3_EMPTY + j), 1); }
+        mbar_init(BAR(M3_DONE), 1); mbar_init(BAR(D3_EMPTY), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&s_tmem)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(sbase + S_TMEM) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -226,7 +243,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     __syncthreads();
     tc_fence_after();
 
-    const uint32_t tmem = s_tmem;
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + S_TMEM);
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);     /* this warp's TMEM lane quarter */
     if (warp >= W_E2 && warp < W_E2 + 4) {
         /* constant A operand of the bias K-step of conv II: k = 0, 1 -> 1.0, k = 2..15 -> 0 */
@@ -238,15 +255,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     __syncthreads();
     tc_fence_after();
 
-    const uint32_t bar0 = smem_u32(&s_bar[0]);
-    auto BAR = [&](int i) -> uint32_t { return bar0 + 8u * (uint32_t)i; };
     const int units = p.bands * p.nsegs;
 
     if (warp < 4) {
         /* ============================ control warpgroup: TMA producer + three MMA issuers ==================== */
-        reg_dec<48>();
+        reg_dec<48>();                      /* the setmaxnreg pool is what the dec's release: 4096 + 2048 + 2048 regs */
         if (warp == W_TMA) {
-            /* Y16 rows of the current unit, 8-row chunks into a 4-stage ring */
+            /* Y16 rows of the current unit, 8-row chunks into a 4-stage ring (rows past the plane are zero-filled) */
             uint32_t ck = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const Unit un = unit_of(p, u);
@@ -258,42 +273,47 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     mbar_wait(BAR(Y_EMPTY + s), (k & 1) ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(BAR(Y_FULL + s), CH_BYTES);
-                        tma_load_2d(smem_u32(sY) + s * CH_BYTES, &ymap, x0, yr0 + j * CH_ROWS, BAR(Y_FULL + s));
+                        tma_load_2d(sY + s * CH_BYTES, &ymap, x0, yr0 + j * CH_ROWS, BAR(Y_FULL + s));
                     }
                     __syncwarp();
                 }
             }
-        } else {
-            /* MMA issuers: warp-uniform control flow, one elected lane issues; the rows of all units form one
-             * continuous stream, the loop is unrolled by two so that buffer index b is a compile-time constant */
-            const int total = total_rows(p, units);
-            if (warp == W_MMA1) {
-                const uint64_t db = umma_desc(smem_u32(sW), 128, (K1 / 8) * 128);
-                auto step = [&](auto B, uint32_t ph) {
-                    constexpr uint32_t b = decltype(B)::value;
-                    mbar_wait(BAR(A1_FULL + b), ph);
-                    mbar_wait(BAR(D1_EMPTY + b), ph ^ 1);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        #pragma unroll
-                        for (int s = 0; s < K1 / 16; s++)
-                            umma_ts(tmem + D1_COL + b * D1_STR, tmem + A1_COL + b * A1_STR + 8 * s, db + 16 * s, umma_idesc(N1), s > 0);
-                        umma_commit(BAR(M1_DONE + b));
+        } else if (warp == W_MMA1) {
+            /* conv I: the A1 window is a ring of 9 row slots, so the weight image rotates with the row (R = n mod 9) */
+            const uint64_t db0 = umma_desc(sW, 128, (K1 / 8) * 128);
+            uint32_t pr = 0;                                               /* global row-pair counter */
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const Unit un = unit_of(p, u);
+                uint32_t R = (uint32_t)(un.ra % 9);   /* weight-image rotation of conv II row q: (q + 2) mod 9 */
+                #pragma unroll 1
+                for (int n = 0; n < un.nrows; n += 2, pr++) {
+                    const uint32_t ph = pr & 1;
+                    #pragma unroll
+                    for (uint32_t b = 0; b < 2; b++) {
+                        mbar_wait(BAR(A1_FULL + b), ph);
+                        mbar_wait(BAR(D1_EMPTY + b), ph ^ 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t db = db0 + (uint64_t)(R * (B1_BYTES >> 4));
+                            #pragma unroll
+                            for (int s = 0; s < K1 / 16; s++)
+                                umma_ts(tmem + D1_COL + b * D1_STR, tmem + A1_COL + b * A1_STR + 8 * s, db + 16 * s, umma_idesc(N1), s > 0);
+                            umma_commit(BAR(M1_DONE + b));
+                        }
+                        __syncwarp();
+                        R = (R == NROT - 1) ? 0 : R + 1;
                     }
-                    __syncwarp();
-                };
-                #pragma unroll 1
-                #pragma unroll 1
-        for (int g = 0; g < total; g += 2) {
-                    const uint32_t ph = (g >> 1) & 1;
-                    step(std::integral_constant<uint32_t, 0>{}, ph);
-                    if (g + 1 < total) step(std::integral_constant<uint32_t, 1>{}, ph);
                 }
-            } else if (warp == W_MMA2) {
-                const uint64_t db = umma_desc(smem_u32(sW) + B1_BYTES, 128, (K2 / 8) * 128);
-                const uint64_t dbb = umma_desc(smem_u32(sW) + B1_BYTES + B2_BYTES + B3_BYTES, 128, 256);
-                auto step = [&](auto B, uint32_t ph) {
-                    constexpr uint32_t b = decltype(B)::value;
+            }
+        } else if (warp == W_MMA2) {
+            const uint64_t db = umma_desc(sW + W_B2, 128, (K2 / 8) * 128);
+            const uint64_t dbb = umma_desc(sW + W_B2B, 128, 256);
+            const int total = total_rows(p, units);
+            #pragma unroll 1
+            for (int g = 0; g < total; g += 2) {
+                const uint32_t ph = (g >> 1) & 1;
+                #pragma unroll
+                for (uint32_t b = 0; b < 2; b++) {
                     mbar_wait(BAR(A2_FULL + b), ph);
                     mbar_wait(BAR(D2_EMPTY + b), ph ^ 1);
                     tc_fence_after();
@@ -305,49 +325,57 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                         umma_commit(BAR(M2_DONE + b));
                     }
                     __syncwarp();
-                };
-                #pragma unroll 1
-                #pragma unroll 1
-        for (int g = 0; g < total; g += 2) {
-                    const uint32_t ph = (g >> 1) & 1;
-                    step(std::integral_constant<uint32_t, 0>{}, ph);
-                    if (g + 1 < total) step(std::integral_constant<uint32_t, 1>{}, ph);
                 }
-            } else {
-                const uint64_t db = umma_desc(smem_u32(sW) + B1_BYTES + B2_BYTES, 128, (K3 / 8) * 128);
-                auto step = [&](auto B, uint32_t ph) {
-                    constexpr uint32_t b = decltype(B)::value;
-                    mbar_wait(BAR(A3_FULL + b), ph);
-                    mbar_wait(BAR(D3_EMPTY + b), ph ^ 1);
+            }
+        } else {
+            /* conv III, dy on the tensor core: one set per pair of output rows (r0, r0+1):
+             *   D3[px][5*o + dx] = sum_{rho<6} sum_ch A3[row clamp(r0-2+rho)][px][ch] * W3[ch][dy = rho-o-2][dx]
+             * the row clamp of the reference (src/libsrcnn.cpp:461-491) is a choice of ring slot per K-step */
+            const uint64_t db3 = umma_desc(sW + W_B3, 128, 256);
+            uint32_t kg0 = 0, sg = 0;                                      /* global pair / set counters */
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const Unit un = unit_of(p, u);
+                #pragma unroll 1
+                for (int pp = 0; pp < un.npairs; pp++, sg++) {
+                    const uint32_t kn = kg0 + (uint32_t)pp + 2;           /* newest pair this set reads */
+                    mbar_wait(BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
+                    mbar_wait(BAR(D3_EMPTY), (sg & 1) ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
+                        const int r0 = un.ra + 2 * pp;
                         #pragma unroll
-                        for (int s = 0; s < K3 / 16; s++)
-                            umma_ts(tmem + D3_COL + b * D3_STR, tmem + A3_COL + b * A3_STR + 8 * s, db + 16 * s, umma_idesc(N3), s > 0);
-                        umma_commit(BAR(M3_DONE + b));
+                        for (int rho = 0; rho < 6; rho++) {
+                            int q = r0 - 2 + rho;
+                            q = q < 0 ? 0 : (q > p.dh - 1 ? p.dh - 1 : q);
+                            const uint32_t slot = (2u * kg0 + (uint32_t)(q - (un.ra - 2))) & 7u;
+                            const uint32_t a = tmem + A3_COL + slot * A3_SLOT;
+                            umma_ts(tmem + D3_COL, a,     db3 + (uint64_t)((2 * rho) * (B3_TILE >> 4)),     umma_idesc(N3), rho > 0);
+                            umma_ts(tmem + D3_COL, a + 8, db3 + (uint64_t)((2 * rho + 1) * (B3_TILE >> 4)), umma_idesc(N3), 1);
+                        }
+                        umma_commit(BAR(M3_DONE));
+                        /* pair kg0+pp is dead after this set; the last set of a unit retires the remaining two */
+                        umma_commit(BAR(A3_EMPTY) + 8u * ((kg0 + (uint32_t)pp) & 3));
+                        if (pp == un.npairs - 1) {
+                            umma_commit(BAR(A3_EMPTY) + 8u * ((kg0 + (uint32_t)pp + 1) & 3));
+                            umma_commit(BAR(A3_EMPTY) + 8u * ((kg0 + (uint32_t)pp + 2) & 3));
+                        }
                     }
                     __syncwarp();
-                };
-                #pragma unroll 1
-                #pragma unroll 1
-        for (int g = 0; g < total; g += 2) {
-                    const uint32_t ph = (g >> 1) & 1;
-                    step(std::integral_constant<uint32_t, 0>{}, ph);
-                    if (g + 1 < total) step(std::integral_constant<uint32_t, 1>{}, ph);
                 }
+                kg0 += (uint32_t)un.npairs + 2;
             }
         }
     } else if (warp < W_E1) {
-        /* ===================== im2col: smem Y16 ring -> rolling 9x10 register window -> A1 in TMEM ========== */
-        reg_inc<128>();
+        /* ===================== im2col: smem Y16 ring -> 9-slot register ring -> A1 in TMEM ==================== */
+        reg_inc<96>();
         const int t = (warp - W_IM2COL) * 32 + lane;
         uint32_t it = 0, ck = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const Unit un = unit_of(p, u);
             const int hw = ((un.band * kBandCols + 2) & 7) + t;       /* half offset of this lane's window in the box */
-            const uint32_t woff = smem_u32(sY) + (uint32_t)(hw >> 1) * 4u, sh = (uint32_t)(hw & 1) * 16u;
+            const uint32_t woff = sY + (uint32_t)(hw >> 1) * 4u, sh = (uint32_t)(hw & 1) * 16u;
             const int last_rho = un.nrows + 7;
-            uint32_t W[9][5];                                         /* rows q-4 .. q+4, two halves per word */
+            uint32_t W[9][5];                                         /* slot s holds Y row (rho mod 9 == s), two halves per word */
             auto fetch = [&](int rho, uint32_t (&w5)[5]) {
                 const uint32_t c = ck + (uint32_t)(rho / CH_ROWS), s = c % NST;
                 if ((rho % CH_ROWS) == 0) mbar_wait(BAR(Y_FULL + s), (c / NST) & 1);
@@ -359,11 +387,15 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 for (int j = 0; j < 5; j++) w5[j] = __funnelshift_r(x[j], x[j + 1], sh);
                 if ((rho % CH_ROWS) == CH_ROWS - 1 || rho == last_rho) warp_arrive(BAR(Y_EMPTY + s), lane);
             };
-            #pragma unroll
-            for (int i = 0; i < 8; i++) fetch(i, W[i]);
-            #pragma unroll 1
-            for (int n = 0; n < un.nrows; n++, it++) {
-                fetch(n + 8, W[8]);
+            /* Y row y always lives in slot (y + 6) mod 9, i.e. the k position of a tap depends on the absolute image row only
+             * (so the FP32 accumulation order -- and the result, bit for bit -- does not depend on how rows are cut into
+             * units or strips).  Row n (q = ra-2+n): the new Y row rho = n+8 lands in slot (ra+n+8) mod 9, window row i sits
+             * in slot (ra+n+i) mod 9 and the MMA issuer picks the weight image rotated by R = (ra+n) mod 9.  The register ->
+             * TMEM column map never moves.  The first 8 passes (n < 0) only fill the window. */
+            auto row = [&](auto RC, int n) {
+                constexpr int R = decltype(RC)::value;
+                fetch(n + 8, W[(R + 8) % 9]);
+                if (n < 0) return;
                 const uint32_t b = it & 1, ph = (it >> 1) & 1;
                 mbar_wait(BAR(M1_DONE) + 8u * b, ph ^ 1);            /* MMA1 of row it-2 has consumed A1[b] */
                 tc_fence_after();
@@ -383,74 +415,82 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 tmem_wait_st();
                 tc_fence_before();
                 warp_arrive(BAR(A1_FULL) + 8u * b, lane);
-                #pragma unroll
-                for (int i = 0; i < 8; i++)                   /* roll the window down one row */
-                    #pragma unroll
-                    for (int j = 0; j < 5; j++) W[i][j] = W[i + 1][j];
+                it++;
+            };
+            int n = -8;
+#define SRCNN_ROW(R) case R: row(std::integral_constant<int, R>{}, n); if (++n == un.nrows) break;
+            switch ((un.ra + 1) % 9) {
+                for (;;) {
+                    SRCNN_ROW(0) SRCNN_ROW(1) SRCNN_ROW(2) SRCNN_ROW(3) SRCNN_ROW(4) SRCNN_ROW(5) SRCNN_ROW(6) SRCNN_ROW(7) SRCNN_ROW(8)
+                }
             }
+#undef SRCNN_ROW
             ck += (uint32_t)((un.nrows + 8 + CH_ROWS - 1) / CH_ROWS);
         }
     } else if (warp < W_E2) {
-        /* ===================== epilogue I: D1 -> ReLU -> FP16 -> A2 (bias is already inside the GEMM) ======== */
+        /* ===================== epilogue I (two groups, one per row parity): D1 -> ReLU -> FP16 -> A2 ========== */
+        reg_inc<88>();
+        const uint32_t b = (uint32_t)(warp - W_E1) >> 2;
         const int total = total_rows(p, units);
-        auto step = [&](auto B, uint32_t ph) {
-            constexpr uint32_t b = decltype(B)::value;
+        const uint32_t d1 = lane_base + D1_COL + b * D1_STR, a2 = lane_base + A2_COL + b * A2_STR;
+        #pragma unroll 1
+        for (int g = 0; g < total; g += 2) {
+            const uint32_t ph = (g >> 1) & 1;
             uint32_t v[64];
-            mbar_wait(BAR(M1_DONE + b), ph);
+            mbar_wait(BAR(M1_DONE) + 8u * b, ph);
             tc_fence_after();
-            tmem_ld32(lane_base + D1_COL + b * D1_STR, v);
-            tmem_ld32(lane_base + D1_COL + b * D1_STR + 32, v + 32);
+            tmem_ld32(d1, v);
+            tmem_ld32(d1 + 32, v + 32);
             tmem_wait_ld();
             tc_fence_before();
-            warp_arrive(BAR(D1_EMPTY + b), lane);
+            warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);
             #pragma unroll
             for (int m = 0; m < 32; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
-            mbar_wait(BAR(M2_DONE + b), ph ^ 1);                      /* MMA2 of row it-2 has consumed A2[b] */
+            mbar_wait(BAR(M2_DONE) + 8u * b, ph ^ 1);                 /* MMA2 of the previous row of this parity has consumed A2[b] */
             tc_fence_after();
-            tmem_st16(lane_base + A2_COL + b * A2_STR, v);
-            tmem_st16(lane_base + A2_COL + b * A2_STR + 16, v + 16);
+            tmem_st16(a2, v);
+            tmem_st16(a2 + 16, v + 16);
             tmem_wait_st();
             tc_fence_before();
-            warp_arrive(BAR(A2_FULL + b), lane);
-        };
-        #pragma unroll 1
-        for (int g = 0; g < total; g += 2) {
-            const uint32_t ph = (g >> 1) & 1;
-            step(std::integral_constant<uint32_t, 0>{}, ph);
-            if (g + 1 < total) step(std::integral_constant<uint32_t, 1>{}, ph);
+            warp_arrive(BAR(A2_FULL) + 8u * b, lane);
         }
     } else if (warp < W_E3) {
-        /* ===================== epilogue II: D2 (bias included) -> ReLU -> FP16 -> A3 ========================= */
-        const int total = total_rows(p, units);
-        auto step = [&](auto B, uint32_t ph) {
-            constexpr uint32_t b = decltype(B)::value;
-            uint32_t v[32];
-            mbar_wait(BAR(M2_DONE + b), ph);
-            tc_fence_after();
-            tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
-            tmem_wait_ld();
-            tc_fence_before();
-            warp_arrive(BAR(D2_EMPTY + b), lane);
-            #pragma unroll
-            for (int m = 0; m < 16; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
-            mbar_wait(BAR(M3_DONE + b), ph ^ 1);
-            tc_fence_after();
-            tmem_st16(lane_base + A3_COL + b * A3_STR, v);
-            tmem_wait_st();
-            tc_fence_before();
-            warp_arrive(BAR(A3_FULL + b), lane);
-        };
-        #pragma unroll 1
-        for (int g = 0; g < total; g += 2) {
-            const uint32_t ph = (g >> 1) & 1;
-            step(std::integral_constant<uint32_t, 0>{}, ph);
-            if (g + 1 < total) step(std::integral_constant<uint32_t, 1>{}, ph);
+        /* ===================== epilogue II: D2 (bias included) -> ReLU -> FP16 -> A3 ring ===================== */
+        reg_dec<64>();
+        uint32_t kg = 0;                                               /* global pair counter */
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const Unit un = unit_of(p, u);
+            #pragma unroll 1
+            for (int k = 0; k < un.npairs + 2; k++, kg++) {
+                const uint32_t ph = kg & 1, js = kg & 3;
+                const uint32_t a3 = lane_base + A3_COL + js * (2 * A3_SLOT);
+                #pragma unroll
+                for (uint32_t b = 0; b < 2; b++) {
+                    uint32_t v[32];
+                    mbar_wait(BAR(M2_DONE + b), ph);
+                    tc_fence_after();
+                    tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    warp_arrive(BAR(D2_EMPTY + b), lane);
+                    #pragma unroll
+                    for (int m = 0; m < 16; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
+                    if (b == 0) {
+                        mbar_wait(BAR(A3_EMPTY) + 8u * js, ((kg >> 2) & 1) ^ 1);   /* every set that read this pair slot is done */
+                        tc_fence_after();
+                    }
+                    tmem_st16(a3 + b * A3_SLOT, v);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                warp_arrive(BAR(A3_FULL) + 8u * js, lane);
+            }
         }
     } else {
-        /* ===================== conv III gather: dy in registers, dx across lanes, bias, clamp, store ========= */
-        reg_inc<112>();
+        /* ===================== conv III gather: dx across lanes, bias, clamp, store (two rows per set) ======== */
+        reg_dec<64>();
         const int t = (warp - W_E3) * 32 + lane;
-        uint32_t it = 0, em = 0;
+        uint32_t sg = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const Unit un = unit_of(p, u);
             const int c0 = un.band * kBandCols - 2, c = c0 + t;
@@ -463,60 +503,30 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 cc -= c0;
                 pidx[d] = d * 128 + (cc < 0 ? 0 : (cc > 127 ? 127 : cc));
             }
-            float acc[5][5];                    /* acc[j][dx]: partial of output row q-2+j */
-            #pragma unroll
-            for (int j = 0; j < 5; j++)
-                #pragma unroll
-                for (int d = 0; d < 5; d++) acc[j][d] = 0.f;
             #pragma unroll 1
-            for (int n = 0; n < un.nrows; n++, it++) {
-                const int q = un.ra - 2 + n;
-                const uint32_t b = it & 1, ph = (it >> 1) & 1;
-                uint32_t z[32];
-                mbar_wait(BAR(M3_DONE) + 8u * b, ph);
+            for (int pp = 0; pp < un.npairs; pp++, sg++) {
+                uint32_t z[16];
+                mbar_wait(BAR(M3_DONE), sg & 1);
                 tc_fence_after();
-                tmem_ld32(lane_base + D3_COL + b * D3_STR, z);
+                tmem_ld16(lane_base + D3_COL, z);
                 tmem_wait_ld();
                 tc_fence_before();
-                warp_arrive(BAR(D3_EMPTY) + 8u * b, lane);
-                if (q > 0 && q < p.dh - 1) {
-                    /* Z row q feeds output row q-2+j with dy = 2-j */
-                    #pragma unroll
-                    for (int j = 0; j < 5; j++)
-                        #pragma unroll
-                        for (int d = 0; d < 5; d++) acc[j][d] += __uint_as_float(z[(4 - j) * 5 + d]);
-                } else if (q >= 0 && q < p.dh) {
-                    /* first / last image row also stands in for the clamped rows above / below it */
-                    #pragma unroll
-                    for (int j = 0; j < 5; j++)
-                        #pragma unroll
-                        for (int dyi = 0; dyi < 5; dyi++) {
-                            const bool on = (dyi == 4 - j) || (q == 0 && dyi < 4 - j) || (q == p.dh - 1 && dyi > 4 - j);
-                            #pragma unroll
-                            for (int d = 0; d < 5; d++) acc[j][d] += on ? __uint_as_float(z[dyi * 5 + d]) : 0.f;
-                        }
-                }
-                /* output row r = q-2 (acc[0]) is complete */
-                const int r = q - 2;
-                if (r >= un.ra && r < un.rb) {
-                    float* P = &sP[em & 1][0][0]; em++;     /* consecutive emissions alternate buffers */
-                    #pragma unroll
-                    for (int d = 0; d < 5; d++) P[d * 128 + t] = acc[0][d];
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (writer) {
-                        float o = cBias3;
-                        #pragma unroll
-                        for (int d = 0; d < 5; d++) o += P[pidx[d]];
-                        o = fminf(fmaxf(o, 0.f), 255.f);
-                        p.out[(size_t)(r - p.row0) * p.dw + c] = o;
-                    }
-                }
+                warp_arrive(BAR(D3_EMPTY), lane);
+                float* P = sP + (sg & 1) * (10 * 128);
                 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                for (int m = 0; m < 10; m++) P[m * 128 + t] = __uint_as_float(z[m]);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (writer) {
+                    const int r = un.ra + 2 * pp;
+                    float o0 = cBias3, o1 = cBias3;
                     #pragma unroll
-                    for (int d = 0; d < 5; d++) acc[j][d] = acc[j + 1][d];
-                #pragma unroll
-                for (int d = 0; d < 5; d++) acc[4][d] = 0.f;
+                    for (int d = 0; d < 5; d++) { o0 += P[pidx[d]]; o1 += P[5 * 128 + pidx[d]]; }
+                    o0 = fminf(fmaxf(o0, 0.f), 255.f);
+                    o1 = fminf(fmaxf(o1, 0.f), 255.f);
+                    float* dst = p.out + (size_t)(r - p.row0) * p.dw + c;
+                    dst[0] = o0;
+                    if (r + 1 < un.rb) dst[p.dw] = o1;
+                }
             }
         }
     }
@@ -549,32 +559,43 @@ int conv_tc_create(ConvTcState** out)
         const __half h = __float2half_rn(v);
         memcpy(img.data() + base + canon_off(n, k, K), &h, 2);
     };
-    /* conv I: k = 10*i + j  <->  tap (i, j) of the 9x9 kernel; k = 90 / 91 carry the bias split into two halves */
-    for (int n = 0; n < N1; n++) {
-        for (int i = 0; i < 9; i++)
-            for (int j = 0; j < 9; j++) put(0, n, 10 * i + j, K1, SRCNN_W1[i * 9 + j][n]);
-        const float b = SRCNN_B1[n];
-        const float hi = __half2float(__float2half_rn(b));
-        put(0, n, 90, K1, hi);
-        put(0, n, 91, K1, b - hi);
-    }
+    /* conv I, image R (rotation): the A1 operand is a ring of 9 row slots, k = 10*s + j for slot s; for an output row with
+     * n mod 9 == R the window row i (Y row q-4+i) sits in slot (R + i) mod 9.  k = 90 / 91 carry the bias (hi / lo). */
+    for (int R = 0; R < NROT; R++)
+        for (int n = 0; n < N1; n++) {
+            const size_t base = (size_t)R * B1_BYTES;
+            for (int i = 0; i < 9; i++)
+                for (int j = 0; j < 9; j++) put(base, n, 10 * ((R + i) % 9) + j, K1, SRCNN_W1[i * 9 + j][n]);
+            const float b = SRCNN_B1[n];
+            const float hi = __half2float(__float2half_rn(b));
+            put(base, n, 90, K1, hi);
+            put(base, n, 91, K1, b - hi);
+        }
     for (int n = 0; n < N2; n++)
-        for (int k = 0; k < K2; k++) put(B1_BYTES, n, k, K2, SRCNN_W2[k][n]);
-    /* conv III: n = tap (dy*5+dx), k = input channel */
-    for (int n = 0; n < 25; n++)
-        for (int k = 0; k < K3; k++) put(B1_BYTES + B2_BYTES, n, k, K3, SRCNN_W3[n][k]);
-
+        for (int k = 0; k < K2; k++) put(W_B2, n, k, K2, SRCNN_W2[k][n]);
     /* conv II bias as a 32 x 16 operand for the constant-1 K-step: k = 0 hi part, k = 1 lo part */
     for (int n = 0; n < N2; n++) {
         const float b = SRCNN_B2[n];
         const float hi = __half2float(__float2half_rn(b));
-        put(B1_BYTES + B2_BYTES + B3_BYTES, n, 0, 16, hi);
-        put(B1_BYTES + B2_BYTES + B3_BYTES, n, 1, 16, b - hi);
+        put(W_B2B, n, 0, 16, hi);
+        put(W_B2B, n, 1, 16, b - hi);
     }
+    /* conv III, one 16 x 16 tile per K-step (rho, h): column n = 5*o + dx of output row r0+o takes conv II row r0-2+rho
+     * with the tap dy+2 = rho - o (zero outside 0..4); k = channel 16*h + kk.  SRCNN_W3[tap = (dy+2)*5 + (dx+2)][ch]. */
+    for (int rho = 0; rho < 6; rho++)
+        for (int h = 0; h < 2; h++)
+            for (int o = 0; o < 2; o++) {
+                const int dyi = rho - o;
+                if (dyi < 0 || dyi > 4) continue;
+                for (int dx = 0; dx < 5; dx++)
+                    for (int kk = 0; kk < 16; kk++)
+                        put(W_B3 + (size_t)(2 * rho + h) * B3_TILE, 5 * o + dx, kk, 16, SRCNN_W3[dyi * 5 + dx][16 * h + kk]);
+            }
 
     cudaError_t e = cudaMalloc(&st->d_wimg, WIMG_BYTES);
     if (e == cudaSuccess) e = cudaMemcpy(st->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(cBias3, &SRCNN_B3, sizeof(float));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) {
         void* fn = nullptr; cudaDriverEntryPointQueryResult q;
         e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
@@ -603,16 +624,17 @@ int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, u
     p.dw = (int)dw; p.dh = (int)dh; p.out = out; p.row0 = (int)row0; p.row1 = (int)row1;
     p.bands = g.bands;
     const int rows = (int)(row1 - row0);
-    /* row segments: pick the count that minimises (waves x rows per unit incl. 4 halo rows + ~8 rows of refill) */
+    /* row segments (even length: output rows are produced in pairs): pick the count that minimises
+     * (waves x rows per unit incl. 4 halo rows + ~8 rows of refill) */
     int best_nsegs = 1; long best_cost = -1;
     for (int ns = 1; ns <= 256 && ns <= rows; ns++) {
-        const int sr = (rows + ns - 1) / ns;
+        const int sr = ((rows + ns - 1) / ns + 1) & ~1;
         const int nsegs = (rows + sr - 1) / sr;
         const long waves = ((long)p.bands * nsegs + num_sms - 1) / num_sms;
         const long cost = waves * (sr + 12);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nsegs = nsegs; }
     }
-    p.seg_rows = (rows + best_nsegs - 1) / best_nsegs;
+    p.seg_rows = ((rows + best_nsegs - 1) / best_nsegs + 1) & ~1;
     p.nsegs = (rows + p.seg_rows - 1) / p.seg_rows;
     p.wimg = st->d_wimg;
 
@@ -628,7 +650,7 @@ int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, u
 
     const int units = p.bands * p.nsegs;
     const int grid = units < num_sms ? units : num_sms;
-    conv_tc_kernel<<<grid, NWARPS * 32, 0, s>>>(p, map);
+    conv_tc_kernel<<<grid, NWARPS * 32, SMEM_BYTES, s>>>(p, map);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { st->err = cudaGetErrorString(e); return 1; }
     return 0;
