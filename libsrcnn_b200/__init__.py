@@ -6,12 +6,14 @@ thin binding the tests and the benchmark use; it contains no image arithmetic an
 is not built, or there is no B200, every entry point raises.
 """
 import ctypes as C
+import os
 import pathlib
 
 import numpy as np
 
 ROOT = pathlib.Path(__file__).resolve().parent
-LIB_PATH = ROOT / "lib" / "libsrcnn.so"
+# SRCNN_B200_LIB: development aid (A/B timing of two builds of the same library); never a different implementation
+LIB_PATH = pathlib.Path(os.environ.get("SRCNN_B200_LIB", ROOT / "lib" / "libsrcnn.so"))
 
 NEAREST, BILINEAR, BICUBIC, LANCZOS3, BSPLINE = range(5)
 CONV_TENSOR, CONV_EXACT = 0, 1

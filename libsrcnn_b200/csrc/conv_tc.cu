@@ -105,9 +105,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
+    /* the suspend-time hint keeps a waiting warp asleep in the barrier unit instead of re-issuing the probe: without it
+     * ~28 % of all issued instructions of this kernel were retry loops competing with the working warps */
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(bar), "r"(parity) : "memory");
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
