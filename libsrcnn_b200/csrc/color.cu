@@ -7,6 +7,7 @@
  * (its x86-64 -O2 build has no FMA contraction), so both kernels are bit-exact against the oracle.
  */
 #include "kernels.h"
+#include "color_math.cuh"
 
 namespace srcnn {
 
@@ -71,22 +72,6 @@ void launch_color_in(const uint8_t* src, size_t npix, unsigned d, float* planes,
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */
-
-__device__ __forceinline__ uint32_t to_u8(float f)
-{
-    /* (unsigned char)MAX(0.f, MIN(255.f, f)) with MIN(a,b) = a<b?a:b, truncating cast */
-    f = (255.f < f) ? 255.f : f;
-    f = (0.f > f) ? 0.f : f;
-    return __float2uint_rz(f);
-}
-
-__device__ __forceinline__ void rgb_of(float y, float cb, float cr, uint32_t& r, uint32_t& g, uint32_t& b)
-{
-    const float fcb = __fsub_rn(cb, 128.f), fcr = __fsub_rn(cr, 128.f);
-    r = to_u8(__fadd_rn(y, __fdiv_rn(__fmul_rn(45.f, fcr), 32.f)));
-    g = to_u8(__fsub_rn(y, __fdiv_rn(__fadd_rn(__fmul_rn(11.f, fcb), __fmul_rn(23.f, fcr)), 32.f)));
-    b = to_u8(__fadd_rn(y, __fdiv_rn(__fmul_rn(113.f, fcb), 64.f)));
-}
 
 template <int D, bool CONV, bool VEC>
 __global__ void __launch_bounds__(256)

@@ -31,13 +31,16 @@
  * keeps |dY'| < 1 (final 8-bit output within 1 LSB); tests/test_parity_gpu.py asserts it against the oracle.
  */
 #include "kernels.h"
+#include "color_math.cuh"
 #include "srcnn_weights_data.h"
 
 #include <cuda.h>
 #include <string>
 #include <vector>
 #include <cstring>
+#include <cstdio>
 #include <type_traits>
+
 
 namespace srcnn {
 
@@ -60,8 +63,10 @@ constexpr uint32_t D1_STR = 64, D2_STR = 32, A1_STR = 48, A2_STR = 32, A3_SLOT =
 constexpr int CH_ROWS = 8, BOX_W = 144, NST = 4;
 constexpr int CH_BYTES = CH_ROWS * BOX_W * 2;
 
-/* warp roles: one control warpgroup + five 4-warp groups (TMEM lane quarter = warp & 3) */
-constexpr int W_TMA = 0, W_MMA1 = 1, W_MMA2 = 2, W_MMA3 = 3, W_IM2COL = 4, W_E1 = 8, W_E2 = 16, W_E3 = 20, NWARPS = 24;
+/* warp roles: one control warpgroup + five 4-warp groups (TMEM lane quarter = warp & 3); the order of the groups made no
+ * measurable difference on B200 */
+constexpr int W_E3 = 0, W_E2 = 4, W_E1 = 8, W_IM2COL = 16, W_CTL = 20, NWARPS = 24;
+constexpr int W_TMA = W_CTL, W_MMA1 = W_CTL + 1, W_MMA2 = W_CTL + 2, W_MMA3 = W_CTL + 3;
 
 /* barrier indices.  M?_DONE[b] fires when the MMAs of layer ? for a row with parity b have completed: it both frees the
  * A operand region for the producer group and publishes the accumulator to the consumer group. */
@@ -70,7 +75,8 @@ enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + 2, D1_E
        A3_FULL = D2_EMPTY + 2, A3_EMPTY = A3_FULL + 4, M3_DONE = A3_EMPTY + 4, D3_EMPTY = M3_DONE + 1, NBAR = D3_EMPTY + 1 };
 
 /* dynamic shared memory layout (offsets from a 1024-byte aligned base) */
-constexpr int S_Y = 0, S_W = NST * CH_BYTES, S_P = S_W + WIMG_BYTES, S_BAR = S_P + 2 * 10 * 128 * 4, S_TMEM = S_BAR + NBAR * 8;
+constexpr int S_Y = 0, S_W = NST * CH_BYTES, S_P = S_W + WIMG_BYTES, S_OUT = S_P + 2 * 10 * 128 * 4, S_BAR = S_OUT + 2 * 2 * 384,
+              S_TMEM = S_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = S_TMEM + 16 + 1024;
 static_assert(S_W % 128 == 0 && S_P % 16 == 0 && S_BAR % 8 == 0, "smem layout");
 
@@ -181,35 +187,63 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane)
 }
 
 /* ---------------------------------------------------------------- the kernel */
+#ifdef SRCNN_PROF
+/* development build: every barrier wait accumulates its duration per call site; CTA 0 dumps (per warp) the totals */
+#define WAITP(id, bar, par) do { const long long t0_ = clock64(); mbar_wait(bar, par); prof_acc[id] += clock64() - t0_; } while (0)
+#else
+#define WAITP(id, bar, par) mbar_wait(bar, par)
+#endif
+
 struct TcParams {
     int pitch, y16_rows;
     int dw, dh;
-    float* out;                 /* rows [row0,row1) x dw */
+    float* out;                 /* FP32 Y', rows [row0,row1) x dw, or NULL */
+    const float *cb, *cr, *al;  /* fused colour-out (rgb != NULL): chroma / alpha planes, u8 outputs; all at row row0 */
+    unsigned char *rgb, *conv8;
+    int d;
     int row0, row1;
-    int bands, seg_rows, nsegs;
+    int bands, ppb;             /* column bands; row pairs per band = ceil((row1-row0) / 2) */
     const unsigned char* wimg;  /* B1 x 9 rotations | B2 | B2-bias | B3 operand images */
+#ifdef SRCNN_PROF
+    long long* prof;
+#endif
 };
 
-/* a work unit = one 128-column band x one row segment [ra, rb).  It streams the conv II rows q = ra-2 .. ra-3+nrows;
- * nrows is even (output rows are produced in pairs; an odd segment computes one discarded extra row). */
+/* Work partition.  The (band, row pair) grid is walked band-major and cut into gridDim.x contiguous spans of equal
+ * length, one per CTA; a span that crosses a band boundary splits into units.  A work unit = one 128-column band x
+ * the rows [ra, rb); it streams the conv II rows q = ra-2 .. ra-3+nrows, nrows even (output rows are produced in
+ * pairs; an odd tail computes one discarded extra row).  Long contiguous units keep the per-unit cost (4 halo rows,
+ * 8 window-fill rows, pipeline fill and drain) to about two per CTA. */
 struct Unit { int band, ra, rb, npairs, nrows; };
-__device__ __forceinline__ Unit unit_of(const TcParams& p, int u)
+struct Span { int s, e, nunits; };
+__device__ __forceinline__ Span span_of(const TcParams& p)
+{
+    const long long T = (long long)p.bands * p.ppb;
+    Span x;
+    x.s = (int)(T * blockIdx.x / gridDim.x);
+    x.e = (int)(T * (blockIdx.x + 1) / gridDim.x);
+    x.nunits = x.e > x.s ? (x.e - 1) / p.ppb - x.s / p.ppb + 1 : 0;
+    return x;
+}
+__device__ __forceinline__ Unit unit_of(const TcParams& p, const Span& sp, int k)
 {
     Unit x;
-    x.band = u % p.bands;
-    const int seg = u / p.bands;
-    x.ra = p.row0 + seg * p.seg_rows;
-    x.rb = min(x.ra + p.seg_rows, p.row1);
-    x.npairs = (x.rb - x.ra + 1) >> 1;
+    x.band = sp.s / p.ppb + k;
+    const int p0 = k == 0 ? sp.s - x.band * p.ppb : 0;
+    const int p1 = min(p.ppb, sp.e - x.band * p.ppb);
+    x.ra = p.row0 + 2 * p0;
+    x.rb = min(p.row0 + 2 * p1, p.row1);
+    x.npairs = p1 - p0;
     x.nrows = 2 * x.npairs + 4;
     return x;
 }
-__device__ __forceinline__ int total_rows(const TcParams& p, int units)
+__device__ __forceinline__ int total_rows(const TcParams& p, const Span& sp)
 {
     int total = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) total += unit_of(p, u).nrows;
+    for (int k = 0; k < sp.nunits; k++) total += unit_of(p, sp, k).nrows;
     return total;
 }
+
 
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
@@ -219,8 +253,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     unsigned char* const sgen = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t sY = sbase + S_Y, sW = sbase + S_W, bar0 = sbase + S_BAR;
     float* const sP = reinterpret_cast<float*>(sgen + S_P);
+    unsigned char* const sOut = sgen + S_OUT;                          /* [set parity][row of the pair][124 px x 3 B] */
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef SRCNN_PROF
+    long long prof_acc[2] = { 0, 0 };
+    const long long prof_t0 = clock64();
+#endif
     auto BAR = [&](int i) -> uint32_t { return bar0 + 8u * (uint32_t)i; };
 
     /* one-time setup: weights -> smem (generic proxy, then made visible to the async proxy), barriers, TMEM */
@@ -257,22 +296,22 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     __syncthreads();
     tc_fence_after();
 
-    const int units = p.bands * p.nsegs;
+    const Span span = span_of(p);
 
-    if (warp < 4) {
+    if (warp >= W_CTL && warp < W_CTL + 4) {
         /* ============================ control warpgroup: TMA producer + three MMA issuers ==================== */
         reg_dec<48>();                      /* the setmaxnreg pool is what the dec's release: 4096 + 2048 + 2048 regs */
         if (warp == W_TMA) {
             /* Y16 rows of the current unit, 8-row chunks into a 4-stage ring (rows past the plane are zero-filled) */
             uint32_t ck = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const Unit un = unit_of(p, u);
+            for (int u = 0; u < span.nunits; u++) {
+                const Unit un = unit_of(p, span, u);
                 const int x0 = (un.band * kBandCols + 2) & ~7;            /* 16 B aligned box origin */
                 const int yr0 = un.ra - p.row0;                           /* plane row of image row ra-6 */
                 const int nch = (un.nrows + 8 + CH_ROWS - 1) / CH_ROWS;
                 for (int j = 0; j < nch; j++, ck++) {
                     const uint32_t s = ck % NST, k = ck / NST;
-                    mbar_wait(BAR(Y_EMPTY + s), (k & 1) ^ 1);
+                    WAITP(0, BAR(Y_EMPTY + s), (k & 1) ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(BAR(Y_FULL + s), CH_BYTES);
                         tma_load_2d(sY + s * CH_BYTES, &ymap, x0, yr0 + j * CH_ROWS, BAR(Y_FULL + s));
@@ -284,16 +323,16 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             /* conv I: the A1 window is a ring of 9 row slots, so the weight image rotates with the row (R = n mod 9) */
             const uint64_t db0 = umma_desc(sW, 128, (K1 / 8) * 128);
             uint32_t pr = 0;                                               /* global row-pair counter */
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const Unit un = unit_of(p, u);
+            for (int u = 0; u < span.nunits; u++) {
+                const Unit un = unit_of(p, span, u);
                 uint32_t R = (uint32_t)(un.ra % 9);   /* weight-image rotation of conv II row q: (q + 2) mod 9 */
                 #pragma unroll 1
                 for (int n = 0; n < un.nrows; n += 2, pr++) {
                     const uint32_t ph = pr & 1;
                     #pragma unroll
                     for (uint32_t b = 0; b < 2; b++) {
-                        mbar_wait(BAR(A1_FULL + b), ph);
-                        mbar_wait(BAR(D1_EMPTY + b), ph ^ 1);
+                        WAITP(0, BAR(A1_FULL + b), ph);
+                        WAITP(1, BAR(D1_EMPTY + b), ph ^ 1);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint64_t db = db0 + (uint64_t)(R * (B1_BYTES >> 4));
@@ -310,14 +349,14 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         } else if (warp == W_MMA2) {
             const uint64_t db = umma_desc(sW + W_B2, 128, (K2 / 8) * 128);
             const uint64_t dbb = umma_desc(sW + W_B2B, 128, 256);
-            const int total = total_rows(p, units);
+            const int total = total_rows(p, span);
             #pragma unroll 1
             for (int g = 0; g < total; g += 2) {
                 const uint32_t ph = (g >> 1) & 1;
                 #pragma unroll
                 for (uint32_t b = 0; b < 2; b++) {
-                    mbar_wait(BAR(A2_FULL + b), ph);
-                    mbar_wait(BAR(D2_EMPTY + b), ph ^ 1);
+                    WAITP(0, BAR(A2_FULL + b), ph);
+                    WAITP(1, BAR(D2_EMPTY + b), ph ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
                         #pragma unroll
@@ -335,13 +374,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
              * the row clamp of the reference (src/libsrcnn.cpp:461-491) is a choice of ring slot per K-step */
             const uint64_t db3 = umma_desc(sW + W_B3, 128, 256);
             uint32_t kg0 = 0, sg = 0;                                      /* global pair / set counters */
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const Unit un = unit_of(p, u);
+            for (int u = 0; u < span.nunits; u++) {
+                const Unit un = unit_of(p, span, u);
                 #pragma unroll 1
                 for (int pp = 0; pp < un.npairs; pp++, sg++) {
                     const uint32_t kn = kg0 + (uint32_t)pp + 2;           /* newest pair this set reads */
-                    mbar_wait(BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
-                    mbar_wait(BAR(D3_EMPTY), (sg & 1) ^ 1);
+                    WAITP(0, BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
+                    WAITP(1, BAR(D3_EMPTY), (sg & 1) ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
                         const int r0 = un.ra + 2 * pp;
@@ -367,20 +406,20 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 kg0 += (uint32_t)un.npairs + 2;
             }
         }
-    } else if (warp < W_E1) {
+    } else if (warp >= W_IM2COL && warp < W_IM2COL + 4) {
         /* ===================== im2col: smem Y16 ring -> 9-slot register ring -> A1 in TMEM ==================== */
         reg_inc<96>();
         const int t = (warp - W_IM2COL) * 32 + lane;
         uint32_t it = 0, ck = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const Unit un = unit_of(p, u);
+        for (int u = 0; u < span.nunits; u++) {
+            const Unit un = unit_of(p, span, u);
             const int hw = ((un.band * kBandCols + 2) & 7) + t;       /* half offset of this lane's window in the box */
             const uint32_t woff = sY + (uint32_t)(hw >> 1) * 4u, sh = (uint32_t)(hw & 1) * 16u;
             const int last_rho = un.nrows + 7;
             uint32_t W[9][5];                                         /* slot s holds Y row (rho mod 9 == s), two halves per word */
             auto fetch = [&](int rho, uint32_t (&w5)[5]) {
                 const uint32_t c = ck + (uint32_t)(rho / CH_ROWS), s = c % NST;
-                if ((rho % CH_ROWS) == 0) mbar_wait(BAR(Y_FULL + s), (c / NST) & 1);
+                if ((rho % CH_ROWS) == 0) WAITP(0, BAR(Y_FULL + s), (c / NST) & 1);
                 const uint32_t a = woff + s * CH_BYTES + (uint32_t)(rho % CH_ROWS) * (BOX_W * 2);
                 uint32_t x[6];
                 #pragma unroll
@@ -399,7 +438,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 fetch(n + 8, W[(R + 8) % 9]);
                 if (n < 0) return;
                 const uint32_t b = it & 1, ph = (it >> 1) & 1;
-                mbar_wait(BAR(M1_DONE) + 8u * b, ph ^ 1);            /* MMA1 of row it-2 has consumed A1[b] */
+                WAITP(1, BAR(M1_DONE) + 8u * b, ph ^ 1);            /* MMA1 of row it-2 has consumed A1[b] */
                 tc_fence_after();
                 const uint32_t dst = lane_base + A1_COL + b * A1_STR;
                 uint32_t r[16];
@@ -429,17 +468,17 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
 #undef SRCNN_ROW
             ck += (uint32_t)((un.nrows + 8 + CH_ROWS - 1) / CH_ROWS);
         }
-    } else if (warp < W_E2) {
+    } else if (warp >= W_E1 && warp < W_E1 + 8) {
         /* ===================== epilogue I (two groups, one per row parity): D1 -> ReLU -> FP16 -> A2 ========== */
         reg_inc<88>();
         const uint32_t b = (uint32_t)(warp - W_E1) >> 2;
-        const int total = total_rows(p, units);
+        const int total = total_rows(p, span);
         const uint32_t d1 = lane_base + D1_COL + b * D1_STR, a2 = lane_base + A2_COL + b * A2_STR;
         #pragma unroll 1
         for (int g = 0; g < total; g += 2) {
             const uint32_t ph = (g >> 1) & 1;
             uint32_t v[64];
-            mbar_wait(BAR(M1_DONE) + 8u * b, ph);
+            WAITP(0, BAR(M1_DONE) + 8u * b, ph);
             tc_fence_after();
             tmem_ld32(d1, v);
             tmem_ld32(d1 + 32, v + 32);
@@ -448,7 +487,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);
             #pragma unroll
             for (int m = 0; m < 32; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
-            mbar_wait(BAR(M2_DONE) + 8u * b, ph ^ 1);                 /* MMA2 of the previous row of this parity has consumed A2[b] */
+            WAITP(1, BAR(M2_DONE) + 8u * b, ph ^ 1);                 /* MMA2 of the previous row of this parity has consumed A2[b] */
             tc_fence_after();
             tmem_st16(a2, v);
             tmem_st16(a2 + 16, v + 16);
@@ -456,12 +495,12 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             tc_fence_before();
             warp_arrive(BAR(A2_FULL) + 8u * b, lane);
         }
-    } else if (warp < W_E3) {
+    } else if (warp >= W_E2 && warp < W_E2 + 4) {
         /* ===================== epilogue II: D2 (bias included) -> ReLU -> FP16 -> A3 ring ===================== */
         reg_dec<64>();
         uint32_t kg = 0;                                               /* global pair counter */
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const Unit un = unit_of(p, u);
+        for (int u = 0; u < span.nunits; u++) {
+            const Unit un = unit_of(p, span, u);
             #pragma unroll 1
             for (int k = 0; k < un.npairs + 2; k++, kg++) {
                 const uint32_t ph = kg & 1, js = kg & 3;
@@ -469,7 +508,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 #pragma unroll
                 for (uint32_t b = 0; b < 2; b++) {
                     uint32_t v[32];
-                    mbar_wait(BAR(M2_DONE + b), ph);
+                    WAITP(0, BAR(M2_DONE + b), ph);
                     tc_fence_after();
                     tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
                     tmem_wait_ld();
@@ -478,7 +517,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     #pragma unroll
                     for (int m = 0; m < 16; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
                     if (b == 0) {
-                        mbar_wait(BAR(A3_EMPTY) + 8u * js, ((kg >> 2) & 1) ^ 1);   /* every set that read this pair slot is done */
+                        WAITP(1, BAR(A3_EMPTY) + 8u * js, ((kg >> 2) & 1) ^ 1);   /* every set that read this pair slot is done */
                         tc_fence_after();
                     }
                     tmem_st16(a3 + b * A3_SLOT, v);
@@ -493,8 +532,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         reg_dec<64>();
         const int t = (warp - W_E3) * 32 + lane;
         uint32_t sg = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const Unit un = unit_of(p, u);
+        for (int u = 0; u < span.nunits; u++) {
+            const Unit un = unit_of(p, span, u);
             const int c0 = un.band * kBandCols - 2, c = c0 + t;
             const bool writer = (t >= 2 && t < 126 && c < p.dw);
             int pidx[5];                        /* lane of column clamp(c + dx) -- conv III clamps its input plane */
@@ -505,10 +544,31 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 cc -= c0;
                 pidx[d] = d * 128 + (cc < 0 ? 0 : (cc > 127 ? 127 : cc));
             }
+            /* RGB (d = 3) rows are staged in shared memory and stored as words when the band's row segment is word-aligned */
+            const bool rgb_staged = p.rgb && p.d == 3 && (p.dw & 3) == 0 && ((uintptr_t)p.rgb & 3u) == 0;
+            const int nvalid = min(kBandCols, p.dw - un.band * kBandCols), nwords = (nvalid * 3) >> 2;
+            float ncb0 = 0.f, ncr0 = 0.f, nal0 = 0.f, ncb1 = 0.f, ncr1 = 0.f, nal1 = 0.f;
+            auto load_chroma = [&](int r) {
+                if (!(writer && p.rgb)) return;
+                const size_t ix = (size_t)(r - p.row0) * p.dw + c;
+                ncb0 = __ldg(p.cb + ix); ncr0 = __ldg(p.cr + ix);
+                if (p.d == 4) nal0 = __ldg(p.al + ix);
+                if (r + 1 < un.rb) {
+                    ncb1 = __ldg(p.cb + ix + p.dw); ncr1 = __ldg(p.cr + ix + p.dw);
+                    if (p.d == 4) nal1 = __ldg(p.al + ix + p.dw);
+                }
+            };
+            load_chroma(un.ra);
             #pragma unroll 1
             for (int pp = 0; pp < un.npairs; pp++, sg++) {
                 uint32_t z[16];
-                mbar_wait(BAR(M3_DONE), sg & 1);
+                const int r = un.ra + 2 * pp;
+                const bool two = r + 1 < un.rb;
+                const size_t pix = (size_t)(r - p.row0) * p.dw + c;
+                /* chroma of this pair was requested one set ago; request the next pair's now (a full set period to land) */
+                const float cb0 = ncb0, cr0 = ncr0, al0 = nal0, cb1 = ncb1, cr1 = ncr1, al1 = nal1;
+                if (pp + 1 < un.npairs) load_chroma(r + 2);
+                WAITP(0, BAR(M3_DONE), sg & 1);
                 tc_fence_after();
                 tmem_ld16(lane_base + D3_COL, z);
                 tmem_wait_ld();
@@ -519,20 +579,55 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 for (int m = 0; m < 10; m++) P[m * 128 + t] = __uint_as_float(z[m]);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (writer) {
-                    const int r = un.ra + 2 * pp;
                     float o0 = cBias3, o1 = cBias3;
                     #pragma unroll
                     for (int d = 0; d < 5; d++) { o0 += P[pidx[d]]; o1 += P[5 * 128 + pidx[d]]; }
                     o0 = fminf(fmaxf(o0, 0.f), 255.f);
                     o1 = fminf(fmaxf(o1, 0.f), 255.f);
-                    float* dst = p.out + (size_t)(r - p.row0) * p.dw + c;
-                    dst[0] = o0;
-                    if (r + 1 < un.rb) dst[p.dw] = o1;
+                    if (p.out) {
+                        float* dst = p.out + pix;
+                        dst[0] = o0;
+                        if (two) dst[p.dw] = o1;
+                    }
+                    if (p.rgb) {
+                        /* memcpy conv III -> Y, convertImgF32XtoImgU8, conv plane (src/libsrcnn.cpp:855-861, 889-915) */
+                        auto emit = [&](float y, float cb, float cr, float al, size_t ix, unsigned char* stage) {
+                            uint32_t R, G, B;
+                            rgb_of(y, cb, cr, R, G, B);
+                            if (p.d == 4) {
+                                reinterpret_cast<uint32_t*>(p.rgb)[ix] = R | (G << 8) | (B << 16) | (to_u8(al) << 24);
+                            } else if (stage) {
+                                stage[0] = (unsigned char)R; stage[1] = (unsigned char)G; stage[2] = (unsigned char)B;
+                            } else {
+                                unsigned char* q = p.rgb + ix * 3;
+                                q[0] = (unsigned char)R; q[1] = (unsigned char)G; q[2] = (unsigned char)B;
+                            }
+                            if (p.conv8) p.conv8[ix] = (unsigned char)__float2uint_rz(y);
+                        };
+                        unsigned char* stg = rgb_staged ? sOut + (sg & 1) * 768 + (t - 2) * 3 : nullptr;
+                        emit(o0, cb0, cr0, al0, pix, stg);
+                        if (two) emit(o1, cb1, cr1, al1, pix + p.dw, stg ? stg + 384 : nullptr);
+                    }
+                }
+                if (rgb_staged) {
+                    /* RGB rows leave as coalesced 32-bit words: 124 px x 3 B = 93 words per row and band */
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (t < nwords) {
+                        const uint32_t* w0 = reinterpret_cast<const uint32_t*>(sOut + (sg & 1) * 768);
+                        uint32_t* g0 = reinterpret_cast<uint32_t*>(p.rgb + ((size_t)(r - p.row0) * p.dw + (c0 + 2)) * 3);
+                        g0[t] = w0[t];
+                        if (two) reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(g0) + (size_t)p.dw * 3)[t] = w0[96 + t];
+                    }
                 }
             }
         }
     }
 
+#ifdef SRCNN_PROF
+    if (blockIdx.x == 0 && lane == 0) {
+        p.prof[warp * 4 + 0] = clock64() - prof_t0; p.prof[warp * 4 + 1] = prof_acc[0]; p.prof[warp * 4 + 2] = prof_acc[1];
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == W_MMA2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
@@ -619,25 +714,19 @@ void conv_tc_destroy(ConvTcState* st)
 const char* conv_tc_error(const ConvTcState* st) { return st ? st->err.c_str() : "no state"; }
 
 int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, unsigned dh,
-                   float* out, unsigned row0, unsigned row1, int num_sms, cudaStream_t s)
+                   float* out, unsigned row0, unsigned row1, int num_sms, cudaStream_t s, const ConvTcColor* col)
 {
     TcParams p;
+    p.cb = col ? col->cb : nullptr; p.cr = col ? col->cr : nullptr; p.al = col ? col->al : nullptr;
+    p.rgb = col ? col->rgb : nullptr; p.conv8 = col ? col->conv8 : nullptr; p.d = col ? (int)col->d : 3;
+    /* the RGBA store is one 32-bit word per pixel */
+    if (p.rgb && p.d == 4 && ((uintptr_t)p.rgb & 3u)) { st->err = "fused colour-out: RGBA output must be 4-byte aligned"; return 1; }
+    if (!out && !p.rgb) { st->err = "no output requested"; return 1; }
     p.pitch = g.pitch; p.y16_rows = g.rows;
     p.dw = (int)dw; p.dh = (int)dh; p.out = out; p.row0 = (int)row0; p.row1 = (int)row1;
     p.bands = g.bands;
     const int rows = (int)(row1 - row0);
-    /* row segments (even length: output rows are produced in pairs): pick the count that minimises
-     * (waves x rows per unit incl. 4 halo rows + ~8 rows of refill) */
-    int best_nsegs = 1; long best_cost = -1;
-    for (int ns = 1; ns <= 256 && ns <= rows; ns++) {
-        const int sr = ((rows + ns - 1) / ns + 1) & ~1;
-        const int nsegs = (rows + sr - 1) / sr;
-        const long waves = ((long)p.bands * nsegs + num_sms - 1) / num_sms;
-        const long cost = waves * (sr + 12);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nsegs = nsegs; }
-    }
-    p.seg_rows = ((rows + best_nsegs - 1) / best_nsegs + 1) & ~1;
-    p.nsegs = (rows + p.seg_rows - 1) / p.seg_rows;
+    p.ppb = (rows + 1) / 2;
     p.wimg = st->d_wimg;
 
     CUtensorMap map;
@@ -650,9 +739,27 @@ int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, u
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { st->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"; return 1; }
 
-    const int units = p.bands * p.nsegs;
-    const int grid = units < num_sms ? units : num_sms;
+    /* one persistent CTA per SM; tiny inputs: at least ~16 row pairs per CTA so that the per-unit costs stay amortised */
+    const long long T = (long long)p.bands * p.ppb, want = (T + 15) / 16;
+    const int grid = (int)(want < 1 ? 1 : (want < num_sms ? want : num_sms));
+#ifdef SRCNN_PROF
+    static long long* d_prof = nullptr;
+    if (!d_prof) cudaMalloc(&d_prof, NWARPS * 4 * 8);
+    p.prof = d_prof;
+#endif
     conv_tc_kernel<<<grid, NWARPS * 32, SMEM_BYTES, s>>>(p, map);
+#ifdef SRCNN_PROF
+    {
+        cudaStreamSynchronize(s);
+        long long h[NWARPS * 4];
+        cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+        static const char* role[6] = { "gather", "E2", "E1.even", "E1.odd", "im2col", "ctl" };
+        static const char* ctl[4] = { "TMA", "MMA1", "MMA2", "MMA3" };
+        for (int w = 0; w < NWARPS; w += (w >= W_CTL ? 1 : 4))
+            fprintf(stderr, "PROF %-8s total %8lld  wait0 %5.1f%%  wait1 %5.1f%%\n", w >= W_CTL ? ctl[w - W_CTL] : role[w / 4], h[w * 4],
+                    100.0 * h[w * 4 + 1] / h[w * 4], 100.0 * h[w * 4 + 2] / h[w * 4]);
+    }
+#endif
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { st->err = cudaGetErrorString(e); return 1; }
     return 0;

@@ -81,8 +81,18 @@ int  conv_exact_init();    /* uploads the FP32 parameter tables to __constant__ 
 struct ConvTcState;                         /* per-context: device weights image, tensor maps */
 int  conv_tc_create(ConvTcState** st);      /* 0 ok */
 void conv_tc_destroy(ConvTcState* st);
+/* optional fused store stage: colour-out of the strip rows straight from the conv III registers (the reference's
+ * memcpy + convertImgF32XtoImgU8 + conv plane, src/libsrcnn.cpp:855-861, 889-915).  All pointers address row `row0`. */
+struct ConvTcColor {
+    const float* cb = nullptr; const float* cr = nullptr; const float* al = nullptr;   /* resized chroma / alpha planes */
+    uint8_t* rgb = nullptr;      /* interleaved u8 result (d = 3 or 4), NULL = no fused colour-out                    */
+    uint8_t* conv8 = nullptr;    /* u8 conv plane or NULL                                                           */
+    unsigned d = 3;
+};
+/* out (FP32 Y', rows [row0,row1) x dw) may be NULL when col.rgb is given */
 int  launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, unsigned dh,
-                    float* out, unsigned row0, unsigned row1, int num_sms, cudaStream_t s);
+                    float* out, unsigned row0, unsigned row1, int num_sms, cudaStream_t s,
+                    const ConvTcColor* col = nullptr);
 const char* conv_tc_error(const ConvTcState* st);
 
 /* colour-out: Y' + Cb/Cr/(A) -> interleaved u8 (+ optional u8 conv plane); all arrays are `npix` long views */
