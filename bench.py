@@ -1,13 +1,16 @@
 #!/usr/bin/env python3
 """bench.py -- throughput of the SRCNN hot path (ProcessSRCNN: colour-in -> resize -> fused conv I/II/III -> colour-out).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
 A step = one pass of the hot path over one synthetic frame per GPU (BASELINE.json configs[1]: 1920x1080 RGB x2.0
 bicubic -> 3840x2160).  Frames are independent units, so N GPUs process N frames per step with no collective
 (weak scaling); torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the timing.
+Other workloads (not the headline; BASELINE configs 3-5): c3 = ONE 7680x4320 RGBA image cut into row strips with a
+6-row halo, one strip per rank (strong scaling); c4 = 512x512 Lanczos-3 frames, a batch per rank; c5 = x1.5 B-spline
+with the convolution plane.
 
 Printed JSON (one line, rank 0):
   value     whole-job output megapixels/s, inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps
@@ -32,12 +35,13 @@ ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-NCU_CONV_DRAM_BYTES = 17079808   # conv_tc_kernel at C2: 17.02 MB read + 0.06 MB written (profiles/r1_ncu_summary.md)
+NCU_CONV_DRAM_BYTES = 17239040   # conv_tc_kernel at C2: 17.18 MB read + 0.06 MB written (profiles/r1_ncu_summary.md)
 FLOP_PER_PX = 16064            # conv I 81*64 + conv II 64*32 + conv III 25*32 MACs, x2
 WORKLOADS = {
     # name: (h, w, d, multiply, filter, description)
     "c2": (1080, 1920, 3, 2.0, 2, "synthetic 1920x1080 RGB x2.0 bicubic -> 3840x2160 (BASELINE configs[1])"),
-    "c4": (512, 512, 3, 2.0, 3, "synthetic 512x512 RGB x2.0 Lanczos-3 -> 1024x1024 (one frame of BASELINE configs[3])"),
+    "c3": (4320, 7680, 4, 2.0, 2, "synthetic 7680x4320 RGBA x2.0 bicubic -> 15360x8640, row strips with 6-row halos (BASELINE configs[2])"),
+    "c4": (512, 512, 3, 2.0, 3, "synthetic 512x512 RGB x2.0 Lanczos-3 -> 1024x1024 frames, batch per GPU (BASELINE configs[3])"),
     "c5": (2160, 3840, 3, 1.5, 4, "synthetic 3840x2160 RGB x1.5 B-spline -> 5760x3240, conv-output on (BASELINE configs[4])"),
 }
 
@@ -51,35 +55,47 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled from a thread every ~2 ms (the timed
+    region of the default run lasts only tens of milliseconds, far below nvidia-smi's own sampling period)"""
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.ok, self.run = [], False, True
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml as N
+            N.nvmlInit()
+            self.N, self.h = N, N.nvmlDeviceGetHandleByIndex(index)
+            self.max = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.ok = True
+            self.t = threading.Thread(target=self._poll, daemon=True); self.t.start()
+        except Exception as e:                                              # noqa: BLE001
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+    def _poll(self):
+        N = self.N
+        while self.run:
+            try:
+                self.rows.append((time.time(), float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)),
+                                  int(N.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception:                                               # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 6] or [r for (_, r) in self.rows if len(r) >= 6]
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "err", "?")]}
+        self.run = False; self.t.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[0]) for r in rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": ["no samples"]}
+        N = self.N
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        names = [("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max,
+                "reasons": [n for n, b in names if bits & b], "samples": len(rows), "source": "NVML, 2 ms period, timed region only"}
 
 
 def cpu_reference_run(h, w, d, m, filt, conv_on, budget_s=12.0):
@@ -136,6 +152,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--conv", default="tensor", choices=["tensor", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU and step (default 1; c4: 32)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -156,18 +173,26 @@ def main():
 
     h, w, d, m, filt, desc = wl
     conv_on = args.workload == "c5"
+    strips = args.workload == "c3"                                  # one image, one row strip per rank (strong scaling)
+    nfr = args.frames or (32 if args.workload == "c4" else 1)       # frames per rank and step (c4: a batch)
+    if strips:
+        nfr = 1
     ow, oh = S.output_dims(w, h, m)
-    out_px = ow * oh
+    r0, r1 = (oh * rank // world, oh * (rank + 1) // world) if strips else (0, oh)
+    out_px = (r1 - r0) * ow * nfr                                   # this rank's output pixels per step
+    job_px = (ow * oh) if strips else ow * oh * nfr * world         # whole-job output pixels per step
     ctx = S.Context(local, S.CONV_TENSOR if args.conv == "tensor" else S.CONV_EXACT)
-    img = O.synth("uniform", h, w, d, 42 + rank)
-    d_src = torch.from_numpy(img).cuda()
-    d_out = torch.empty((oh, ow, d), dtype=torch.uint8, device="cuda")
-    d_conv = torch.empty((oh, ow), dtype=torch.uint8, device="cuda") if conv_on else None
+    imgs = np.stack([O.synth("uniform", h, w, d, (43 if strips else 42 + rank * nfr + i)) for i in range(nfr)])
+    d_src = torch.from_numpy(imgs).cuda()
+    d_out = torch.empty((nfr, r1 - r0, ow, d), dtype=torch.uint8, device="cuda")
+    d_conv = torch.empty((nfr, r1 - r0, ow), dtype=torch.uint8, device="cuda") if conv_on else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
 
     def step():
-        ctx.pass_device(d_src.data_ptr(), w, h, d, m, filt, d_out.data_ptr(), d_conv.data_ptr() if conv_on else 0)
+        for i in range(nfr):
+            ctx.pass_device(d_src[i].data_ptr(), w, h, d, m, filt, d_out[i].data_ptr(),
+                            d_conv[i].data_ptr() if conv_on else 0, rows=(r0, r1))
 
     def barrier():
         torch.cuda.synchronize()
@@ -184,8 +209,8 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     conv_ms, stage_ms = [], []
     launches0 = ctx.launches
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
     t_wall0 = time.time()
     for i in range(args.steps):
         with torch.cuda.stream(stream):
@@ -194,7 +219,7 @@ def main():
         step()
         ev[i][1].record(stream)
         ctx.sync()                                                         # also collects the per-kernel events
-        t = ctx.timings(); conv_ms.append(t["conv"]); stage_ms.append(t)
+        t = ctx.timings(); conv_ms.append(t["conv"]); stage_ms.append(t)   # (of the step's last frame)
     barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
@@ -205,31 +230,38 @@ def main():
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms_max = float(tmax.item())
-    value = out_px * world * args.steps / (total_ms_max * 1e-3) / 1e6
+    value = job_px * args.steps / (total_ms_max * 1e-3) / 1e6
 
     # ---- end to end: the C-ABI call with pinned host buffers (H2D + kernels + D2H inside the timed region)
-    h_src = S.pinned_empty((h, w, d)); h_src[...] = img
-    h_out = S.pinned_empty((oh, ow, d)); h_conv = S.pinned_empty((oh, ow)) if conv_on else None
+    h_src = S.pinned_empty((nfr, h, w, d)); h_src[...] = imgs
+    h_out = S.pinned_empty((nfr, r1 - r0, ow, d)); h_conv = S.pinned_empty((nfr, r1 - r0, ow)) if conv_on else None
+
+    def e2e_step():
+        if nfr > 1:
+            ctx.batch(h_src, m, filt, conv_on, out=h_out, conv=h_conv)
+        else:
+            ctx.pass_host(h_src[0], m, filt, conv_on, rows=(r0, r1), out=h_out[0], conv=h_conv[0] if conv_on else None)
+
     for _ in range(2):
-        ctx.pass_host(h_src, m, filt, conv_on, out=h_out, conv=h_conv)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.pass_host(h_src, m, filt, conv_on, out=h_out, conv=h_conv)
+        e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = out_px * world * args.steps / float(te.item()) / 1e6
-    # the drop-in C++ call itself (pageable new[] output), rank 0, for reference
+    e2e_val = job_px * args.steps / float(te.item()) / 1e6
+    # the drop-in C++ call itself (pageable input, new[] output released with delete[]), rank 0, for reference
     dropin = None
-    if rank == 0:
-        S.process_srcnn(img, m, filt, False, conv_on)
+    if rank == 0 and not strips:
+        S.process_srcnn(imgs[0], m, filt, False, conv_on, copy=False)
         t0 = time.perf_counter(); n = max(3, args.steps // 4)
         for _ in range(n):
-            rc, _, _ = S.process_srcnn(img, m, filt, False, conv_on)
-        dropin = out_px * n / (time.perf_counter() - t0) / 1e6 if rc == 0 else None
+            rc, _, _ = S.process_srcnn(imgs[0], m, filt, False, conv_on, copy=False)
+        dropin = ow * oh * n / (time.perf_counter() - t0) / 1e6 if rc == 0 else None
 
     if rank != 0:
         if dist is not None:
@@ -237,8 +269,14 @@ def main():
         return
 
     pk = peaks()
+    if strips:                                                     # source rows each rank uploads (strip + halo), summed
+        h2d_bytes = sum((lambda g: (g[1][1] - g[1][0]) * w * d)(S.strip_geometry(w, h, d, m, filt, oh * k // world, oh * (k + 1) // world))
+                        for k in range(world))
+    else:
+        h2d_bytes = int(imgs.nbytes)
     conv_avg_ms = float(np.mean(conv_ms))
-    achieved_tf = out_px * FLOP_PER_PX / (conv_avg_ms * 1e-3) / 1e12
+    conv_px = (r1 - r0) * ow                                       # one launch = one frame (or strip) of this rank
+    achieved_tf = conv_px * FLOP_PER_PX / (conv_avg_ms * 1e-3) / 1e12
     stage_avg = {k: float(np.mean([s[k] for s in stage_ms])) for k in stage_ms[0]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -246,15 +284,19 @@ def main():
     line = {
         "metric": "output MP/s, SRCNN x2 to 4K (ProcessSRCNN hot path)", "value": value, "unit": "output MP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if strips else "weak", "vs_baseline": None,
         "dtype": "f16 operands / f32 accumulate (conv), f64 (resize), f32 (colour)" if args.conv == "tensor" else "f32 (conv exact mode), f64 (resize)",
         "data": "synthetic",
-        "config": {"workload": desc, "frames_per_step": world, "sharding": "one frame per GPU, no collective",
+        "config": {"workload": desc, "frames_per_step": 1 if strips else world * nfr,
+                   "sharding": ("row strips [oh*g/N, oh*(g+1)/N) with a recomputed 6-row halo, no collective" if strips
+                                else "%d frame(s) per GPU and step, no collective" % nfr),
                    "conv_mode": args.conv, "l2": "256 MiB buffer written between timed steps (L2 flush)",
                    "conv_output": conv_on},
-        "e2e": {"value": e2e_val, "unit": "output MP/s", "h2d_bytes_per_step": int(img.nbytes) * world,
-                "d2h_bytes_per_step": (out_px * d + (out_px if conv_on else 0)) * world,
-                "api": "srcnn_b200_pass_host (C-ABI, pinned host buffers)", "dropin_ProcessSRCNN_pageable": dropin},
+        "e2e": {"value": e2e_val, "unit": "output MP/s",
+                "h2d_bytes_per_step": h2d_bytes * (1 if strips else world),
+                "d2h_bytes_per_step": job_px * d + (job_px if conv_on else 0),
+                "api": "srcnn_b200_%s (C-ABI, pinned host buffers)" % ("batch_host" if nfr > 1 else "pass_host_rows" if strips else "pass_host"),
+                "dropin_ProcessSRCNN_pageable": dropin},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "fused conv I+II+III (%s)" % args.conv, "bound": "tensor", "achieved": achieved_tf,
@@ -262,7 +304,7 @@ def main():
                      "traffic": NCU_CONV_DRAM_BYTES if (args.workload == "c2" and args.conv == "tensor") else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r1_ncu_summary.md); the 33 MB Y' write stays in L2",
                      "peak_source": pk["src"], "kernel_ms": conv_avg_ms,
-                     "algorithmic_flop_per_launch": out_px * FLOP_PER_PX},
+                     "algorithmic_flop_per_launch": conv_px * FLOP_PER_PX},
         "stage_ms": stage_avg,
         "cpu_baseline": cpu,
     }

@@ -133,8 +133,11 @@ int srcnn_b200_contrib_table(int filter, unsigned dst, unsigned src, int* left, 
 
 /* The compact form of the same table that the fused front-end kernel reads: per destination index `cwin` in-bounds
  * taps starting at cleft, with the exactly-zero weights of the reference's window trimmed away (adding +-0 to the
- * accumulator changes nothing).  *exact29 = 1 if every weight has <= 29 significant bits (its product with an FP32
- * sample is then exact in double).  Returns cwin, 0 if the source is narrower than the window, -1 if maxwin is too small. */
+ * accumulator changes nothing).  *exact29 is a bit set: bit 0 = every weight has <= 29 significant bits (its product
+ * with an FP32 sample is then exact in double); bit 1 = "pow2pair": cwin == 2, both weights exact in FP32 and one of each
+ * pair 0 or a power of two (bilinear at x2), which lets the kernel resample chroma / alpha in FP32 with one fused
+ * multiply-add per sample, bit-identically.  Returns cwin, 0 if the source is narrower than the window, -1 if maxwin is
+ * too small. */
 int srcnn_b200_contrib_table_compact(int filter, unsigned dst, unsigned src, int* cleft, double* weights, int maxwin,
                                      int* exact29);
 

@@ -119,14 +119,15 @@ def contrib_table(filt, dst, src, maxwin=64):
     return L, R, W
 
 
-def contrib_table_compact(filt, dst, src, maxwin=16):
-    """compact form read by the fused front-end kernel -> (cwin, cleft, weights[dst, maxwin], exact29); cwin 0 = none"""
+def contrib_table_compact(filt, dst, src, maxwin=16, flags=False):
+    """compact form read by the fused front-end kernel -> (cwin, cleft, weights[dst, maxwin], exact29); cwin 0 = none.
+    flags=True returns the raw bit set instead of exact29 (bit 0 exact29, bit 1 pow2pair)"""
     L = np.zeros(dst, np.int32); W = np.zeros((dst, maxwin), np.float64); ex = C.c_int(0)
     win = lib().srcnn_b200_contrib_table_compact(int(filt), dst, src, L.ctypes.data_as(_i32p), W.ctypes.data_as(_f64p),
                                                  maxwin, C.byref(ex))
     if win < 0:
         raise SrcnnError(win, "contrib_table_compact")
-    return win, L, W, bool(ex.value)
+    return win, L, W, (ex.value if flags else bool(ex.value & 1))
 
 
 def _vp(a):
@@ -235,13 +236,16 @@ class Context:
             return rc, None, None
         return rc, out, conv
 
-    def batch(self, frames, multiply, filt=BICUBIC, want_conv=False, out=None):
+    def batch(self, frames, multiply, filt=BICUBIC, want_conv=False, out=None, conv=None):
         n, h, w, d = frames.shape
         frames = np.ascontiguousarray(frames, np.uint8)
         ow, oh = output_dims(w, h, multiply)
         if out is None:
             out = np.empty((n, oh, ow, d), np.uint8)
-        conv = np.empty((n, oh, ow), np.uint8) if want_conv else None
+        if not want_conv:
+            conv = None
+        elif conv is None:
+            conv = np.empty((n, oh, ow), np.uint8)
         self._ck(self.L.srcnn_b200_batch_host(self.h, _vp(frames), n, w, h, d, multiply, int(filt), _vp(out), _vp(conv)),
                  "batch_host")
         return out, conv

@@ -122,6 +122,7 @@ void build_axis_table(int filter, unsigned dst, unsigned src, AxisTable& t)
     }
     t.cwin = (widest + 1) / 2 * 2;
     t.compact = (int)src >= t.cwin;
+    t.pow2pair = false;
     if (t.compact) {
         t.cleft.assign(dst, 0); t.cw.assign((size_t)dst * t.cwin, 0.0);
         for (unsigned u = 0; u < dst; u++) {
@@ -129,6 +130,15 @@ void build_axis_table(int filter, unsigned dst, unsigned src, AxisTable& t)
             if (cl + t.cwin > (int)src) cl = (int)src - t.cwin;
             t.cleft[u] = cl;
             for (int i = first[u]; i <= lastnz[u]; i++) t.cw[(size_t)u * t.cwin + (i - cl)] = t.w[(size_t)u * t.win + (i - t.left[u])];
+        }
+        if (t.cwin == 2) {
+            auto f32_exact = [](double v) { return (double)(float)v == v; };
+            auto pow2_or_zero = [](double v) { uint64_t b; memcpy(&b, &v, 8); return v == 0 || (v > 0 && (b & ((1ull << 52) - 1)) == 0); };
+            t.pow2pair = true;
+            for (unsigned u = 0; u < dst && t.pow2pair; u++) {
+                const double a = t.cw[2 * (size_t)u], b = t.cw[2 * (size_t)u + 1];
+                if (!f32_exact(a) || !f32_exact(b) || !(pow2_or_zero(a) || pow2_or_zero(b)) || a < 0 || b < 0) t.pow2pair = false;
+            }
         }
     }
 }

@@ -24,6 +24,9 @@ struct AxisTable {
      * so leaving them out is bit-identical.  exact29: every weight has at most 29 significant bits, so its product
      * with an FP32 sample is exact in double and a fused multiply-add equals the reference's multiply then add. */
     bool compact = false, exact29 = false;
+    /* pow2pair: compact window of 2, both weights exactly representable in FP32 and at least one of each pair 0 or a power
+     * of two (bilinear at x2: 0.25 / 0.75): fmaf(wA, vA, wB * vB) in FP32 is then the correctly rounded exact value */
+    bool pow2pair = false;
     int cwin = 0;
     std::vector<int>    cleft;
     std::vector<double> cw;

@@ -23,6 +23,7 @@ struct AxisTableDev {
     const double* cw;
     int           cwin;
     int           exact29;  /* all weights have <= 29 significant bits: fma == mul, add */
+    int           pow2pair; /* cwin == 2, both weights exact in FP32, one of each pair 0 or a power of two (prep.cu) */
 };
 
 /* geometry of the FP16 conv-input plane consumed by the tensor-core kernel (see DESIGN.md "Y16 plane") */

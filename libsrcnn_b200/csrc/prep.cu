@@ -20,11 +20,19 @@
  * contrib.h), and where every weight of a table has <= 29 significant bits (bilinear at x2: 0.25 / 0.75) the product
  * with an FP32 sample is exact, so one fused multiply-add gives the same double as multiply-then-add.  Shared memory
  * holds the planes as doubles: the (exact) float -> double conversion is paid once per element instead of per tap.
+ *
+ * Third identity (chroma mode 2, "pow2pair" tables: two taps, both weights exact in FP32 and one of them 0 or a power
+ * of two -- bilinear at x2: 0.25 / 0.75, 1 / 0 at the borders): the product with the power-of-two weight is exact in
+ * FP32, so fmaf(wA, vA, wB * vB) rounds the EXACT value wA*vA + wB*vB once to FP32.  The reference's double
+ * accumulation of the same two products is exact as well (samples derived from 8-bit data span < 40 bits), and its
+ * cast to float is that same single rounding.  Cb / Cr / A then need no FP64 at all: they are kept interleaved as
+ * FP32 in shared memory and both resampling passes run once for all of them.
  */
 #include "kernels.h"
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 namespace srcnn {
 
@@ -32,6 +40,9 @@ namespace {
 
 constexpr int TH = 32, TW = 128, NT = 256, NW = NT / 32;
 constexpr int RPT = TH / (NT / TW);        /* destination rows per thread in the horizontal pass */
+
+/* development switch (A/B timing and parity of the two chroma paths) */
+inline bool getenv_flag(const char* name) { const char* e = std::getenv(name); return e && *e && *e != '0'; }
 
 struct PrepParams {
     const uint8_t* src;         /* source row src_row0 */
@@ -117,13 +128,62 @@ __device__ __forceinline__ void hpass(const double* __restrict__ t, const double
     }
 }
 
-template <int D, int WY, int WC, bool CFMA, int SC>
+
+/* ---- chroma mode 2: two-tap FP32 resampling of NC interleaved planes (see the header comment) ---- */
+__device__ __forceinline__ bool pow2_or_zero(float w) { return (__float_as_uint(w) & 0x7FFFFFu) == 0u; }
+/* value = fmaf(wA, vA, wB * vB) with B the tap whose weight is 0 or a power of two */
+__device__ __forceinline__ float mix2(float wA, float vA, float wB, float vB) { return __fmaf_rn(wA, vA, __fmul_rn(wB, vB)); }
+
+template <int NC> struct CVec;
+template <> struct CVec<2> { float2 v; };
+template <> struct CVec<3> { float v[3]; };
+
+template <int NC>
+__device__ __forceinline__ void cmix(const float* __restrict__ a, const float* __restrict__ b, float wA, float wB, float (&o)[NC])
+{
+    if (NC == 2) {
+        const float2 va = *reinterpret_cast<const float2*>(a), vb = *reinterpret_cast<const float2*>(b);
+        o[0] = mix2(wA, va.x, wB, vb.x); o[1] = mix2(wA, va.y, wB, vb.y);
+    } else {
+        #pragma unroll
+        for (int k = 0; k < NC; k++) o[k] = mix2(wA, a[k], wB, b[k]);
+    }
+}
+
+/* vertical pass, shared -> shared: warp = destination row, lanes = footprint columns */
+template <int NC, int SC>
+__device__ __forceinline__ void vpass_c32(const float* __restrict__ S, float* __restrict__ T, int nc, int ny,
+                                          const int* __restrict__ vl, const double* __restrict__ vw, int warp, int lane)
+{
+    #pragma unroll 1
+    for (int y = warp; y < ny; y += NW) {
+        const float w0 = (float)vw[2 * y], w1 = (float)vw[2 * y + 1];
+        const bool sw = !pow2_or_zero(w1);                     /* tap 1 is the general one -> A = tap 1, B = tap 0 */
+        const float wA = sw ? w1 : w0, wB = sw ? w0 : w1;
+        const float* sA = S + (size_t)(vl[y] + (sw ? 1 : 0)) * (SC * NC);
+        const float* sB = S + (size_t)(vl[y] + (sw ? 0 : 1)) * (SC * NC);
+        float* t = T + (size_t)y * (SC * NC);
+        #pragma unroll 3
+        for (int c = lane; c < nc; c += 32) {
+            float o[NC];
+            cmix<NC>(sA + c * NC, sB + c * NC, wA, wB, o);
+            if (NC == 2) *reinterpret_cast<float2*>(t + c * NC) = make_float2(o[0], o[1]);
+            else { for (int k = 0; k < NC; k++) t[c * NC + k] = o[k]; }
+        }
+    }
+}
+
+template <int D, int WY, int WC, int CM, int SC>
 __global__ void __launch_bounds__(NT)
 prep_kernel(const PrepParams p)
 {
+    constexpr bool CFMA = (CM == 1);
+    constexpr bool C32 = (CM == 2);                   /* chroma / alpha as interleaved FP32 (pow2pair tables) */
+    constexpr int NC = D - 1;
     extern __shared__ double sm[];
-    double* S = sm;                                   /* [D][SR][SC]  colour-converted source footprint */
-    double* T = sm + D * p.SR * SC;                   /* [TH][SC]     one plane after the vertical pass */
+    double* S = sm;                                   /* [D][SR][SC]  colour-converted source footprint (C32: plane 0 only) */
+    double* T = sm + (C32 ? 1 : D) * p.SR * SC;       /* [TH][SC]     one plane after the vertical pass (C32: NC floats / element) */
+    float* Sc = reinterpret_cast<float*>(T + (C32 && NC == 3 ? 2 : 1) * TH * SC);   /* C32: [SR][SC][NC] FP32 Cb, Cr, (A) */
     __shared__ int s_lim[4];
     __shared__ int s_vl[2][TH];                       /* this tile's rows of the vertical tables */
     __shared__ double s_vwy[TH * WY], s_vwc[TH * WC];
@@ -186,8 +246,15 @@ prep_kernel(const PrepParams p)
                     float y, cb_, cr;
                     ycbcr_of((float)v[k][0], (float)v[k][1], (float)v[k][2], y, cb_, cr);
                     if (c < nc) {
-                        s[c] = (double)y; s[pl + c] = (double)cb_; s[2 * pl + c] = (double)cr;
-                        if (D == 4) s[3 * pl + c] = (double)(float)v[k][D - 1];
+                        s[c] = (double)y;
+                        if (C32) {
+                            float* q = Sc + ((size_t)r * SC + c) * NC;
+                            if (NC == 2) *reinterpret_cast<float2*>(q) = make_float2(cb_, cr);
+                            else { q[0] = cb_; q[1] = cr; q[2] = (float)v[k][D - 1]; }
+                        } else {
+                            s[pl + c] = (double)cb_; s[2 * pl + c] = (double)cr;
+                            if (D == 4) s[3 * pl + c] = (double)(float)v[k][D - 1];
+                        }
                     }
                 }
             }
@@ -257,51 +324,95 @@ prep_kernel(const PrepParams p)
     }
 
     /* 3. planes 1 .. D-1 (Cb, Cr, A): bilinear / box tables */
-    const double* tc = T + rbeg * SC + (hlc - clo);
-    #pragma unroll 1
-    for (int pl = 1; pl < D; pl++) {
-        vpass<WC, CFMA, SC>(S + pl * SR * SC, T, nc, ny, s_vl[1], s_vwc, warp, lane);
+    if (C32) {
+        float* Tc = reinterpret_cast<float*>(T);
+        vpass_c32<NC, SC>(Sc, Tc, nc, ny, s_vl[1], s_vwc, warp, lane);
         __syncthreads();
         if (col_ok) {
-            float* out = p.planes + pl * p.plane_stride + (size_t)(gy0 + rbeg - p.e0) * p.ow + gx;
-            const unsigned ow = p.ow;
-            hpass<WC, CFMA, SC>(tc, wc, nrows, [&](int r, float v) { out[(size_t)r * ow] = v; });
+            const float w0 = (float)wc[0], w1 = (float)wc[1];
+            const bool sw = !pow2_or_zero(w1);
+            const float wA = sw ? w1 : w0, wB = sw ? w0 : w1;
+            const float* tA = Tc + ((size_t)rbeg * SC + (hlc - clo) + (sw ? 1 : 0)) * NC;
+            const float* tB = Tc + ((size_t)rbeg * SC + (hlc - clo) + (sw ? 0 : 1)) * NC;
+            float* out = p.planes + p.plane_stride + (size_t)(gy0 + rbeg - p.e0) * p.ow + gx;
+            const size_t ps = p.plane_stride; const unsigned ow = p.ow;
+            auto body = [&](int r) {
+                float o[NC];
+                cmix<NC>(tA + (size_t)r * (SC * NC), tB + (size_t)r * (SC * NC), wA, wB, o);
+                #pragma unroll
+                for (int k = 0; k < NC; k++) out[k * ps + (size_t)r * ow] = o[k];
+            };
+            if (nrows == RPT) {
+                #pragma unroll 8
+                for (int r = 0; r < RPT; r++) body(r);
+            } else {
+                #pragma unroll 1
+                for (int r = 0; r < nrows; r++) body(r);
+            }
         }
-        __syncthreads();
+    } else {
+        const double* tc = T + rbeg * SC + (hlc - clo);
+        #pragma unroll 1
+        for (int pl = 1; pl < D; pl++) {
+            vpass<WC, CFMA, SC>(S + pl * SR * SC, T, nc, ny, s_vl[1], s_vwc, warp, lane);
+            __syncthreads();
+            if (col_ok) {
+                float* out = p.planes + pl * p.plane_stride + (size_t)(gy0 + rbeg - p.e0) * p.ow + gx;
+                const unsigned ow = p.ow;
+                hpass<WC, CFMA, SC>(tc, wc, nrows, [&](int r, float v) { out[(size_t)r * ow] = v; });
+            }
+            __syncthreads();
+        }
     }
 }
 
-template <int D, int WY, int WC, bool CFMA, int SC>
+/* dynamic shared memory of one CTA (bytes) */
+inline size_t prep_smem(int d, int cm, int SR, int SC)
+{
+    if (cm == 2) return ((size_t)SR + (d == 4 ? 2 : 1) * TH) * SC * sizeof(double) + (size_t)SR * SC * (d - 1) * sizeof(float);
+    return ((size_t)d * SR + TH) * SC * sizeof(double);
+}
+
+template <int D, int WY, int WC, int CM, int SC>
 int launch_one(const PrepParams& p, dim3 grid, cudaStream_t s)
 {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(prep_kernel<D, WY, WC, CFMA, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(prep_kernel<D, WY, WC, CM, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
             cudaGetLastError(); return 0;
         }
         configured = true;
     }
-    const size_t smem = ((size_t)D * p.SR + TH) * SC * sizeof(double);
-    prep_kernel<D, WY, WC, CFMA, SC><<<grid, NT, smem, s>>>(p);
+    prep_kernel<D, WY, WC, CM, SC><<<grid, NT, prep_smem(D, CM, p.SR, SC), s>>>(p);
     return 1;
 }
 
 /* shared-memory row pitch (doubles): 72 covers magnifications >= 2 (128/2 + window), 104 those >= 1.5 */
-template <int D, int WY, bool CFMA>
+template <int D, int WY, int CM>
 int launch_sc(const PrepParams& p, dim3 grid, cudaStream_t s)
 {
-    if (p.SC <= 72)  return launch_one<D, WY, 2, CFMA, 72>(p, grid, s);
-    if (p.SC <= 104) return launch_one<D, WY, 2, CFMA, 104>(p, grid, s);
+    if (p.SC <= 72)  return launch_one<D, WY, 2, CM, 72>(p, grid, s);
+    if (p.SC <= 104) return launch_one<D, WY, 2, CM, 104>(p, grid, s);
     return 0;                                        /* shallower magnification: the separate kernels */
 }
 
+template <int D, int WY>
+int launch_cm(const PrepParams& p, int cm, dim3 grid, cudaStream_t s)
+{
+    switch (cm) {
+        case 2:  return launch_sc<D, WY, 2>(p, grid, s);
+        case 1:  return launch_sc<D, WY, 1>(p, grid, s);
+        default: return launch_sc<D, WY, 0>(p, grid, s);
+    }
+}
+
 template <int D>
-int launch_d(const PrepParams& p, int wy, bool cfma, dim3 grid, cudaStream_t s)
+int launch_d(const PrepParams& p, int wy, int cm, dim3 grid, cudaStream_t s)
 {
     switch (wy) {
-        case 2:  return cfma ? launch_sc<D, 2, true>(p, grid, s) : launch_sc<D, 2, false>(p, grid, s);
-        case 4:  return cfma ? launch_sc<D, 4, true>(p, grid, s) : launch_sc<D, 4, false>(p, grid, s);
-        default: return cfma ? launch_sc<D, 6, true>(p, grid, s) : launch_sc<D, 6, false>(p, grid, s);
+        case 2:  return launch_cm<D, 2>(p, cm, grid, s);
+        case 4:  return launch_cm<D, 4>(p, cm, grid, s);
+        default: return launch_cm<D, 6>(p, cm, grid, s);
     }
 }
 
@@ -345,12 +456,13 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
     p.vyw = vy.cw; p.vcw = vc.cw; p.hyw = hy.cw; p.hcw = hc.cw;
     p.SR = max_footprint(h_vyl, vy.cwin, h_vcl, vc.cwin, e0, e1, TH);
     p.SC = max_footprint(h_hyl, hy.cwin, h_hcl, hc.cwin, 0, ow, TW);
-    if (((size_t)d * p.SR + TH) * 104 * sizeof(double) > 160 * 1024) return 0;
+    /* chroma arithmetic: 2 = FP32 two-tap (pow2pair tables), 1 = FP64 fused multiply-add (exact29), 0 = FP64 mul + add */
+    const int cm = (vc.pow2pair && hc.pow2pair && !getenv_flag("SRCNN_B200_PREP_F64")) ? 2 : (vc.exact29 && hc.exact29) ? 1 : 0;
+    if (prep_smem((int)d, cm, p.SR, 104) > 160 * 1024) return 0;
     if ((size_t)oh * 8 >= (size_t)INT_MAX || (size_t)ow * 8 >= (size_t)INT_MAX) return 0;
     dim3 grid((ow + TW - 1) / TW, (e1 - e0 + TH - 1) / TH);
     if (grid.y > 65535u) return 0;
-    const bool cfma = vc.exact29 && hc.exact29;
-    return d == 3 ? launch_d<3>(p, vy.cwin, cfma, grid, s) : launch_d<4>(p, vy.cwin, cfma, grid, s);
+    return d == 3 ? launch_d<3>(p, vy.cwin, cm, grid, s) : launch_d<4>(p, vy.cwin, cm, grid, s);
 }
 
 } // namespace srcnn

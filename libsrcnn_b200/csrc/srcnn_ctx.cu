@@ -229,6 +229,7 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     t->view.cw    = h.compact ? reinterpret_cast<const double*>(base + ints_al + 2 * wbytes) : nullptr;
     t->view.cwin  = h.cwin;
     t->view.exact29 = h.exact29 ? 1 : 0;
+    t->view.pow2pair = h.pow2pair ? 1 : 0;
     ctx->tables[key] = t;
     *out = t;
     return 0;
@@ -936,7 +937,7 @@ int srcnn_b200_contrib_table_compact(int filter, unsigned dst, unsigned src, int
         cleft[u] = t.cleft[u];
         for (int i = 0; i < maxwin; i++) weights[(size_t)u * maxwin + i] = i < t.cwin ? t.cw[(size_t)u * t.cwin + i] : 0.0;
     }
-    if (exact29) *exact29 = t.exact29 ? 1 : 0;
+    if (exact29) *exact29 = (t.exact29 ? 1 : 0) | (t.pow2pair ? 2 : 0);
     return t.cwin;
 }
 

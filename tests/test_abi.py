@@ -93,6 +93,17 @@ def test_compact_table_is_the_reference_table_minus_exact_zeros(filt, dst, src):
     assert exact29 == bool(((bits & np.uint64((1 << 24) - 1)) == 0).all())
     if filt == S.BILINEAR and dst == 2 * src:
         assert exact29          # 0.25 / 0.75: the fused multiply-add shortcut applies to the chroma planes at x2
+    # pow2pair (FP32 chroma path of the fused front end): two taps, FP32-exact, one of each pair 0 or a power of two
+    flags = S.contrib_table_compact(filt, dst, src, flags=True)[3]
+    w2 = cw[:, :cwin]
+    man = lambda a: (a.copy().view(np.uint64) & np.uint64((1 << 52) - 1)) == 0          # 0 or a power of two
+    want = cwin == 2 and bool((w2.astype(np.float32).astype(np.float64) == w2).all()) and bool((w2 >= 0).all()) \
+        and bool((man(w2[:, 0]) | man(w2[:, 1])).all())
+    assert bool(flags & 2) == want
+    if filt in (S.BILINEAR, S.NEAREST) and dst == 2 * src:
+        assert flags & 2
+    if filt == S.BILINEAR and (dst, src) == (5760, 3840):
+        assert not flags & 2    # x1.5: thirds are not FP32-exact
 
 
 def test_argument_validation_needs_no_gpu():
