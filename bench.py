@@ -121,6 +121,9 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is the OpenMP CPU code with ALL host threads.
+    # (Set before the OpenMP runtime is loaded: nothing below has imported torch or the oracle library yet.)
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     h, w, d, m, filt, desc = wl
     conv_on = args.workload == "c5"
     vals = []

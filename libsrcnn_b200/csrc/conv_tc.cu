@@ -46,6 +46,10 @@ namespace srcnn {
 
 namespace {
 
+#ifndef SRCNN_E2_DECOUPLE
+#define SRCNN_E2_DECOUPLE 0   /* 1: epilogue II drains both rows of a pair before waiting for the A3 slot (measured: no gain) */
+#endif
+
 constexpr int K1 = 96, N1 = 64, NROT = 9;  /* conv I   GEMM; NROT rotated weight images (the A1 window is a ring of 9 row slots) */
 constexpr int K2 = 64, N2 = 32;            /* conv II  GEMM (+ one K=16 step against a constant-1 operand that adds the bias) */
 constexpr int N3 = 16, KS3 = 12;           /* conv III GEMM per PAIR of output rows: K = 6 rows x 32 ch = 12 K-steps, N = 2 rows x 5 dx */
@@ -117,6 +121,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
                  "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
+/* latency-critical waits (the single-lane MMA issuers): poll instead of suspending -- a suspended warp resumes noticeably
+ * later than the phase flips, and that wake-up latency sits on every operand / accumulator hand-over of the pipeline */
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
@@ -147,6 +159,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* r)
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
                  :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                     "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                    "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                    "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* r)
 {
@@ -187,11 +208,16 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane)
 }
 
 /* ---------------------------------------------------------------- the kernel */
+#ifndef SRCNN_SPIN
+#define SRCNN_SPIN 0        /* 1: the MMA issuers poll; 2: the epilogue groups' accumulator-ready waits poll as well */
+#endif
 #ifdef SRCNN_PROF
 /* development build: every barrier wait accumulates its duration per call site; CTA 0 dumps (per warp) the totals */
 #define WAITP(id, bar, par) do { const long long t0_ = clock64(); mbar_wait(bar, par); prof_acc[id] += clock64() - t0_; } while (0)
+#define WAITS(lvl, id, bar, par) do { const long long t0_ = clock64(); if (SRCNN_SPIN >= lvl) mbar_wait_spin(bar, par); else mbar_wait(bar, par); prof_acc[id] += clock64() - t0_; } while (0)
 #else
 #define WAITP(id, bar, par) mbar_wait(bar, par)
+#define WAITS(lvl, id, bar, par) do { if (SRCNN_SPIN >= lvl) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
 #endif
 
 struct TcParams {
@@ -331,8 +357,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     const uint32_t ph = pr & 1;
                     #pragma unroll
                     for (uint32_t b = 0; b < 2; b++) {
-                        WAITP(0, BAR(A1_FULL + b), ph);
-                        WAITP(1, BAR(D1_EMPTY + b), ph ^ 1);
+                        WAITS(1, 0, BAR(A1_FULL + b), ph);
+                        WAITS(1, 1, BAR(D1_EMPTY + b), ph ^ 1);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint64_t db = db0 + (uint64_t)(R * (B1_BYTES >> 4));
@@ -355,8 +381,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 const uint32_t ph = (g >> 1) & 1;
                 #pragma unroll
                 for (uint32_t b = 0; b < 2; b++) {
-                    WAITP(0, BAR(A2_FULL + b), ph);
-                    WAITP(1, BAR(D2_EMPTY + b), ph ^ 1);
+                    WAITS(1, 0, BAR(A2_FULL + b), ph);
+                    WAITS(1, 1, BAR(D2_EMPTY + b), ph ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
                         #pragma unroll
@@ -379,8 +405,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 #pragma unroll 1
                 for (int pp = 0; pp < un.npairs; pp++, sg++) {
                     const uint32_t kn = kg0 + (uint32_t)pp + 2;           /* newest pair this set reads */
-                    WAITP(0, BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
-                    WAITP(1, BAR(D3_EMPTY), (sg & 1) ^ 1);
+                    WAITS(1, 0, BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
+                    WAITS(1, 1, BAR(D3_EMPTY), (sg & 1) ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
                         const int r0 = un.ra + 2 * pp;
@@ -478,7 +504,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         for (int g = 0; g < total; g += 2) {
             const uint32_t ph = (g >> 1) & 1;
             uint32_t v[64];
-            WAITP(0, BAR(M1_DONE) + 8u * b, ph);
+            WAITS(2, 0, BAR(M1_DONE) + 8u * b, ph);
             tc_fence_after();
             tmem_ld32(d1, v);
             tmem_ld32(d1 + 32, v + 32);
@@ -497,7 +523,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         }
     } else if (warp >= W_E2 && warp < W_E2 + 4) {
         /* ===================== epilogue II: D2 (bias included) -> ReLU -> FP16 -> A3 ring ===================== */
+#if SRCNN_E2_DECOUPLE
+        reg_inc<96>();                      /* holds a whole pair (32 + 32 registers); pool: 4096 + 2048 released = 3 x 2048 taken */
+#else
         reg_dec<64>();
+#endif
         uint32_t kg = 0;                                               /* global pair counter */
         for (int u = 0; u < span.nunits; u++) {
             const Unit un = unit_of(p, span, u);
@@ -505,10 +535,31 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             for (int k = 0; k < un.npairs + 2; k++, kg++) {
                 const uint32_t ph = kg & 1, js = kg & 3;
                 const uint32_t a3 = lane_base + A3_COL + js * (2 * A3_SLOT);
+#if SRCNN_E2_DECOUPLE
+                /* both rows of the pair leave D2 (and release it to the conv II issuer) BEFORE the wait for the A3 ring slot:
+                 * a late conv III set then stalls only this group, not conv II two rows ahead */
+                uint32_t h[32];                                                /* the pair's two A3 slots are adjacent columns */
                 #pragma unroll
                 for (uint32_t b = 0; b < 2; b++) {
                     uint32_t v[32];
-                    WAITP(0, BAR(M2_DONE + b), ph);
+                    WAITS(2, 0, BAR(M2_DONE + b), ph);
+                    tc_fence_after();
+                    tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    warp_arrive(BAR(D2_EMPTY + b), lane);
+                    #pragma unroll
+                    for (int m = 0; m < 16; m++) h[16 * b + m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
+                }
+                WAITP(1, BAR(A3_EMPTY) + 8u * js, ((kg >> 2) & 1) ^ 1);       /* every set that read this pair slot is done */
+                tc_fence_after();
+                static_assert(A3_SLOT == 16, "one 32-column store covers the pair");
+                tmem_st32(a3, h);
+#else
+                #pragma unroll
+                for (uint32_t b = 0; b < 2; b++) {
+                    uint32_t v[32];
+                    WAITS(2, 0, BAR(M2_DONE + b), ph);
                     tc_fence_after();
                     tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
                     tmem_wait_ld();
@@ -522,6 +573,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     }
                     tmem_st16(a3 + b * A3_SLOT, v);
                 }
+#endif
                 tmem_wait_st();
                 tc_fence_before();
                 warp_arrive(BAR(A3_FULL) + 8u * js, lane);
@@ -568,7 +620,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 /* chroma of this pair was requested one set ago; request the next pair's now (a full set period to land) */
                 const float cb0 = ncb0, cr0 = ncr0, al0 = nal0, cb1 = ncb1, cr1 = ncr1, al1 = nal1;
                 if (pp + 1 < un.npairs) load_chroma(r + 2);
-                WAITP(0, BAR(M3_DONE), sg & 1);
+                WAITS(2, 0, BAR(M3_DONE), sg & 1);
                 tc_fence_after();
                 tmem_ld16(lane_base + D3_COL, z);
                 tmem_wait_ld();

@@ -153,6 +153,40 @@ def test_interpolated_plane_and_network_output(ctx, filt):
     assert np.array_equal(gyp, yprime)
 
 
+@pytest.mark.parametrize("d,hw,filt", [(3, (61, 83), S.BICUBIC), (4, (47, 130), S.LANCZOS3), (3, (200, 333), S.BSPLINE),
+                                       (4, (9, 5), S.BILINEAR), (3, (33, 64), S.NEAREST)])
+def test_chroma_planes_fp32_path_bit_exact(ctx, d, hw, filt):
+    """Cb / Cr / A at x2 go through the front end's FP32 two-tap path (weights 0.25 / 0.75 / 1: fmaf(wA, vA, wB*vB) is the
+    correctly rounded exact sum, the same value the reference's double accumulation yields).  Checked against the
+    oracle's FP64 resize and against the kernel's own FP64 chroma path (SRCNN_B200_PREP_F64=1), border tiles, odd
+    sizes and strips included."""
+    import os
+    h, w = hw
+    img = O.synth("uniform", h, w, d, 77)
+    o = O.best()
+    planes = o.color_in(img)
+    fc = S.NEAREST if filt == S.NEAREST else S.BILINEAR
+    want = [o.resize(planes[k], 2 * w, 2 * h, fc) for k in range(1, d)]
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    got = {}
+    for mode in ("f32", "f64"):
+        if mode == "f64":
+            os.environ["SRCNN_B200_PREP_F64"] = "1"
+        try:
+            ctx.pass_host(img, 2.0, filt)
+            got[mode] = [ctx.get_plane(k, (2 * h, 2 * w))[1] for k in range(1, d)]
+        finally:
+            os.environ.pop("SRCNN_B200_PREP_F64", None)
+    for k in range(d - 1):
+        assert np.array_equal(got["f32"][k], want[k]), "plane %d: FP32 path differs from the oracle" % (k + 1)
+        assert np.array_equal(got["f64"][k], want[k]), "plane %d: FP64 path differs from the oracle" % (k + 1)
+    # a strip in the middle: rows [r0-6, r1+6) of the planes, same values
+    r0, r1 = (2 * h) // 3, (2 * h) // 3 + max(1, (2 * h) // 4)
+    ctx.pass_host(img, 2.0, filt, rows=(r0, r1))
+    a, pl = ctx.get_plane(1, (2 * h, 2 * w))
+    assert np.array_equal(pl, want[0][a:a + pl.shape[0]])
+
+
 def test_dropin_cpp_api_matches_oracle():
     """ConfigureFilterSRCNN + ProcessSRCNN by their mangled names, new[] ownership, conv plane optional"""
     img = O.synth("uniform", 48, 64, 4, 8)
