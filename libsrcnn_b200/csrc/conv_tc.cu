@@ -59,9 +59,14 @@ constexpr int W_B2 = NROT * B1_BYTES, W_B2B = W_B2 + B2_BYTES, W_B3 = W_B2B + B2
 constexpr int WIMG_BYTES = W_B3 + B3_BYTES;
 
 /* TMEM columns (512 allocated).  D1/D2/A1/A2 are double-buffered by row parity, A3 is a ring of 8 conv II rows
- * (4 pair slots), D3 is single-buffered (one set per two output rows). */
-constexpr uint32_t D1_COL = 0, D2_COL = 128, A2_COL = 192, A1_COL = 256, A3_COL = 352, D3_COL = 480, AC_COL = 496;
-constexpr uint32_t D1_STR = 64, D2_STR = 32, A1_STR = 48, A2_STR = 32, A3_SLOT = 16;
+ * (4 pair slots), D3 is double-buffered by set parity (one set per two output rows). */
+constexpr uint32_t D1_COL = 0, D2_COL = 128, A2_COL = 192, A1_COL = 256, A3_COL = 352, D3_COL = 480;
+constexpr uint32_t D1_STR = 64, D2_STR = 32, A1_STR = 48, A2_STR = 32, A3_SLOT = 16, D3_STR = 16;
+/* conv II bias K-step: its A operand is the LAST K-step of the conv I operand, A1[b] columns 40..47 = k 80..95: k = 90, 91
+ * are the constant 1.0 inputs (the bias sits at those k in the B image), every other k meets a zero weight there.  The
+ * values under the zero weights are Y samples (finite), whichever row im2col has in flight, so the product is exactly 0. */
+constexpr uint32_t ABIAS_OFF = 40;
+constexpr int KBIAS = 10;                  /* k (within that K-step) of the first constant-1 element */
 
 /* Y16 staging ring */
 constexpr int CH_ROWS = 8, BOX_W = 144, NST = 4;
@@ -76,7 +81,7 @@ constexpr int W_TMA = W_CTL, W_MMA1 = W_CTL + 1, W_MMA2 = W_CTL + 2, W_MMA3 = W_
  * A operand region for the producer group and publishes the accumulator to the consumer group. */
 enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + 2, D1_EMPTY = M1_DONE + 2,
        A2_FULL = D1_EMPTY + 2, M2_DONE = A2_FULL + 2, D2_EMPTY = M2_DONE + 2,
-       A3_FULL = D2_EMPTY + 2, A3_EMPTY = A3_FULL + 4, M3_DONE = A3_EMPTY + 4, D3_EMPTY = M3_DONE + 1, NBAR = D3_EMPTY + 1 };
+       A3_FULL = D2_EMPTY + 2, A3_EMPTY = A3_FULL + 4, M3_DONE = A3_EMPTY + 4, D3_EMPTY = M3_DONE + 2, NBAR = D3_EMPTY + 2 };
 
 /* dynamic shared memory layout (offsets from a 1024-byte aligned base) */
 constexpr int S_Y = 0, S_W = NST * CH_BYTES, S_P = S_W + WIMG_BYTES, S_OUT = S_P + 2 * 10 * 128 * 4, S_BAR = S_OUT + 2 * 2 * 384,
@@ -99,11 +104,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 /* instruction descriptor: D = F32, A = B = F16, both K-major, M = 128 */
 __device__ __forceinline__ constexpr uint32_t umma_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
 
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+/* The descriptor is handed over as two 32-bit words: only the low one (address and LBO fields) varies between K-steps
+ * and weight images, the high one (SBO, descriptor version) is a compile-time constant per operand -- this keeps the
+ * single issuing lane's address arithmetic 32-bit (it sits on the pipeline's critical path) */
+__device__ __forceinline__ constexpr uint32_t umma_desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t bdesc_hi, uint32_t idesc, uint32_t accumulate)
 {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
-                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    asm volatile("{\n.reg .pred p;\n.reg .b64 bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 bd, {%2, %3};\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n}\n"
+                 :: "r"(d_tmem), "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
@@ -149,6 +158,18 @@ __device__ __forceinline__ void tmem_wait_ld()    { asm volatile("tcgen05.wait::
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 
+__device__ __forceinline__ void tmem_st1(uint32_t addr, uint32_t r0)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(addr), "r"(r0) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t addr, uint32_t r0, uint32_t r1)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" :: "r"(addr), "r"(r0), "r"(r1) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* r)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -208,16 +229,23 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane)
 }
 
 /* ---------------------------------------------------------------- the kernel */
-#ifndef SRCNN_SPIN
-#define SRCNN_SPIN 0        /* 1: the MMA issuers poll; 2: the epilogue groups' accumulator-ready waits poll as well */
+/* Per-site choice of the wait flavour (development switch, A/B measured): bit set = poll (mbarrier.test_wait) instead of
+ * the suspending try_wait.  Sites: 0 MMA1.A1_FULL  1 MMA1.D1_EMPTY  2 im2col.M1_DONE  3 epilogueI.M1_DONE  4 MMA2.A2_FULL
+ * 5 MMA2.D2_EMPTY  6 epilogueI.M2_DONE  7 epilogueII.M2_DONE  8 MMA3.A3_FULL  9 MMA3.D3_EMPTY  10 gather.M3_DONE */
+#ifndef SRCNN_SPINMASK
+#define SRCNN_SPINMASK 0
 #endif
 #ifdef SRCNN_PROF
 /* development build: every barrier wait accumulates its duration per call site; CTA 0 dumps (per warp) the totals */
 #define WAITP(id, bar, par) do { const long long t0_ = clock64(); mbar_wait(bar, par); prof_acc[id] += clock64() - t0_; } while (0)
-#define WAITS(lvl, id, bar, par) do { const long long t0_ = clock64(); if (SRCNN_SPIN >= lvl) mbar_wait_spin(bar, par); else mbar_wait(bar, par); prof_acc[id] += clock64() - t0_; } while (0)
+#define WAITS(site, id, bar, par) do { const long long t0_ = clock64(); if ((SRCNN_SPINMASK >> (site)) & 1) mbar_wait_spin(bar, par); else mbar_wait(bar, par); prof_acc[id] += clock64() - t0_; } while (0)
 #else
 #define WAITP(id, bar, par) mbar_wait(bar, par)
-#define WAITS(lvl, id, bar, par) do { if (SRCNN_SPIN >= lvl) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
+#define WAITS(site, id, bar, par) do { if ((SRCNN_SPINMASK >> (site)) & 1) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
+#endif
+/* 1: im2col rewrites only the two ring slots (10 TMEM columns) that changed since the same-parity row two rows earlier */
+#ifndef SRCNN_A1_PARTIAL
+#define SRCNN_A1_PARTIAL 1
 #endif
 
 struct TcParams {
@@ -298,7 +326,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             mbar_init(BAR(A2_FULL + b), 4); mbar_init(BAR(M2_DONE + b), 1); mbar_init(BAR(D2_EMPTY + b), 4);
         }
         for (int j = 0; j < 4; j++) { mbar_init(BAR(A3_FULL + j), 4); mbar_init(BAR(A3_EMPTY + j), 1); }
-        mbar_init(BAR(M3_DONE), 1); mbar_init(BAR(D3_EMPTY), 4);
+        for (int b = 0; b < 2; b++) { mbar_init(BAR(M3_DONE + b), 1); mbar_init(BAR(D3_EMPTY + b), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA2) {
@@ -312,16 +340,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
 
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + S_TMEM);
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);     /* this warp's TMEM lane quarter */
-    if (warp >= W_E2 && warp < W_E2 + 4) {
-        /* constant A operand of the bias K-step of conv II: k = 0, 1 -> 1.0, k = 2..15 -> 0 */
-        uint32_t r[8] = { 0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u };
-        tmem_st8(lane_base + AC_COL, r);
-        tmem_wait_st();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
     const Span span = span_of(p);
 
     if (warp >= W_CTL && warp < W_CTL + 4) {
@@ -347,7 +365,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             }
         } else if (warp == W_MMA1) {
             /* conv I: the A1 window is a ring of 9 row slots, so the weight image rotates with the row (R = n mod 9) */
-            const uint64_t db0 = umma_desc(sW, 128, (K1 / 8) * 128);
+            const uint32_t db0 = (uint32_t)umma_desc(sW, 128, (K1 / 8) * 128);
+            constexpr uint32_t dh1 = umma_desc_hi((K1 / 8) * 128);
             uint32_t pr = 0;                                               /* global row-pair counter */
             for (int u = 0; u < span.nunits; u++) {
                 const Unit un = unit_of(p, span, u);
@@ -357,14 +376,14 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     const uint32_t ph = pr & 1;
                     #pragma unroll
                     for (uint32_t b = 0; b < 2; b++) {
-                        WAITS(1, 0, BAR(A1_FULL + b), ph);
+                        WAITS(0, 0, BAR(A1_FULL + b), ph);
                         WAITS(1, 1, BAR(D1_EMPTY + b), ph ^ 1);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint64_t db = db0 + (uint64_t)(R * (B1_BYTES >> 4));
+                            const uint32_t db = db0 + R * (B1_BYTES >> 4);
                             #pragma unroll
                             for (int s = 0; s < K1 / 16; s++)
-                                umma_ts(tmem + D1_COL + b * D1_STR, tmem + A1_COL + b * A1_STR + 8 * s, db + 16 * s, umma_idesc(N1), s > 0);
+                                umma_ts(tmem + D1_COL + b * D1_STR, tmem + A1_COL + b * A1_STR + 8 * s, db + 16 * s, dh1, umma_idesc(N1), s > 0);
                             umma_commit(BAR(M1_DONE + b));
                         }
                         __syncwarp();
@@ -373,22 +392,23 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 }
             }
         } else if (warp == W_MMA2) {
-            const uint64_t db = umma_desc(sW + W_B2, 128, (K2 / 8) * 128);
-            const uint64_t dbb = umma_desc(sW + W_B2B, 128, 256);
+            const uint32_t db = (uint32_t)umma_desc(sW + W_B2, 128, (K2 / 8) * 128);
+            const uint32_t dbb = (uint32_t)umma_desc(sW + W_B2B, 128, 256);
+            constexpr uint32_t dh2 = umma_desc_hi((K2 / 8) * 128), dhb = umma_desc_hi(256);
             const int total = total_rows(p, span);
             #pragma unroll 1
             for (int g = 0; g < total; g += 2) {
                 const uint32_t ph = (g >> 1) & 1;
                 #pragma unroll
                 for (uint32_t b = 0; b < 2; b++) {
-                    WAITS(1, 0, BAR(A2_FULL + b), ph);
-                    WAITS(1, 1, BAR(D2_EMPTY + b), ph ^ 1);
+                    WAITS(4, 0, BAR(A2_FULL + b), ph);
+                    WAITS(5, 1, BAR(D2_EMPTY + b), ph ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
                         #pragma unroll
                         for (int s = 0; s < K2 / 16; s++)
-                            umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR + 8 * s, db + 16 * s, umma_idesc(N2), s > 0);
-                        umma_ts(tmem + D2_COL + b * D2_STR, tmem + AC_COL, dbb, umma_idesc(N2), 1);     /* + bias */
+                            umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR + 8 * s, db + 16 * s, dh2, umma_idesc(N2), s > 0);
+                        umma_ts(tmem + D2_COL + b * D2_STR, tmem + A1_COL + b * A1_STR + ABIAS_OFF, dbb, dhb, umma_idesc(N2), 1);     /* + bias */
                         umma_commit(BAR(M2_DONE + b));
                     }
                     __syncwarp();
@@ -398,28 +418,44 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             /* conv III, dy on the tensor core: one set per pair of output rows (r0, r0+1):
              *   D3[px][5*o + dx] = sum_{rho<6} sum_ch A3[row clamp(r0-2+rho)][px][ch] * W3[ch][dy = rho-o-2][dx]
              * the row clamp of the reference (src/libsrcnn.cpp:461-491) is a choice of ring slot per K-step */
-            const uint64_t db3 = umma_desc(sW + W_B3, 128, 256);
+            const uint32_t db3 = (uint32_t)umma_desc(sW + W_B3, 128, 256);
+            constexpr uint32_t dh3 = umma_desc_hi(256);
             uint32_t kg0 = 0, sg = 0;                                      /* global pair / set counters */
             for (int u = 0; u < span.nunits; u++) {
                 const Unit un = unit_of(p, span, u);
                 #pragma unroll 1
                 for (int pp = 0; pp < un.npairs; pp++, sg++) {
                     const uint32_t kn = kg0 + (uint32_t)pp + 2;           /* newest pair this set reads */
-                    WAITS(1, 0, BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
-                    WAITS(1, 1, BAR(D3_EMPTY), (sg & 1) ^ 1);
+                    WAITS(8, 0, BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
+                    WAITS(9, 1, BAR(D3_EMPTY + (sg & 1)), ((sg >> 1) & 1) ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
                         const int r0 = un.ra + 2 * pp;
-                        #pragma unroll
-                        for (int rho = 0; rho < 6; rho++) {
-                            int q = r0 - 2 + rho;
-                            q = q < 0 ? 0 : (q > p.dh - 1 ? p.dh - 1 : q);
-                            const uint32_t slot = (2u * kg0 + (uint32_t)(q - (un.ra - 2))) & 7u;
-                            const uint32_t a = tmem + A3_COL + slot * A3_SLOT;
-                            umma_ts(tmem + D3_COL, a,     db3 + (uint64_t)((2 * rho) * (B3_TILE >> 4)),     umma_idesc(N3), rho > 0);
-                            umma_ts(tmem + D3_COL, a + 8, db3 + (uint64_t)((2 * rho + 1) * (B3_TILE >> 4)), umma_idesc(N3), 1);
+                        const uint32_t d3 = tmem + D3_COL + (sg & 1) * D3_STR;
+                        if (r0 >= 2 && r0 + 3 < p.dh) {
+                            /* interior set (all but the first and last of an image): the six rows are three consecutive
+                             * pair slots of the ring, no clamping -- the short instruction path matters because this single
+                             * lane issues 12 MMAs per set on the pipeline's critical loop */
+                            const uint32_t kp = kg0 + (uint32_t)pp;
+                            #pragma unroll
+                            for (int j = 0; j < 3; j++) {
+                                const uint32_t pa = tmem + A3_COL + ((kp + j) & 3u) * (2 * A3_SLOT);
+                                #pragma unroll
+                                for (int h = 0; h < 4; h++)
+                                    umma_ts(d3, pa + 8 * h, db3 + (uint32_t)((4 * j + h) * (B3_TILE >> 4)), dh3, umma_idesc(N3), (j | h) > 0);
+                            }
+                        } else {
+                            #pragma unroll
+                            for (int rho = 0; rho < 6; rho++) {
+                                int q = r0 - 2 + rho;
+                                q = q < 0 ? 0 : (q > p.dh - 1 ? p.dh - 1 : q);
+                                const uint32_t slot = (2u * kg0 + (uint32_t)(q - (un.ra - 2))) & 7u;
+                                const uint32_t a = tmem + A3_COL + slot * A3_SLOT;
+                                umma_ts(d3, a,     db3 + (uint32_t)((2 * rho) * (B3_TILE >> 4)),     dh3, umma_idesc(N3), rho > 0);
+                                umma_ts(d3, a + 8, db3 + (uint32_t)((2 * rho + 1) * (B3_TILE >> 4)), dh3, umma_idesc(N3), 1);
+                            }
                         }
-                        umma_commit(BAR(M3_DONE));
+                        umma_commit(BAR(M3_DONE + (sg & 1)));
                         /* pair kg0+pp is dead after this set; the last set of a unit retires the remaining two */
                         umma_commit(BAR(A3_EMPTY) + 8u * ((kg0 + (uint32_t)pp) & 3));
                         if (pp == un.npairs - 1) {
@@ -464,21 +500,39 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 fetch(n + 8, W[(R + 8) % 9]);
                 if (n < 0) return;
                 const uint32_t b = it & 1, ph = (it >> 1) & 1;
-                WAITP(1, BAR(M1_DONE) + 8u * b, ph ^ 1);            /* MMA1 of row it-2 has consumed A1[b] */
+                WAITS(2, 1, BAR(M1_DONE) + 8u * b, ph ^ 1);         /* MMA1 of row it-2 has consumed A1[b] */
                 tc_fence_after();
                 const uint32_t dst = lane_base + A1_COL + b * A1_STR;
-                uint32_t r[16];
-                #pragma unroll
-                for (int m = 0; m < 16; m++) r[m] = W[m / 5][m % 5];
-                tmem_st16(dst, r);
-                #pragma unroll
-                for (int m = 0; m < 16; m++) r[m] = W[(m + 16) / 5][(m + 16) % 5];
-                tmem_st16(dst + 16, r);
-                #pragma unroll
-                for (int m = 0; m < 13; m++) r[m] = W[(m + 32) / 5][(m + 32) % 5];
-                r[13] = 0x3C003C00u;                          /* k = 90, 91: constant 1.0 (bias inputs) */
-                r[14] = 0u; r[15] = 0u;
-                tmem_st16(dst + 32, r);
+                if (!SRCNN_A1_PARTIAL || n < 2) {
+                    /* first two rows of a unit: the whole operand (both parity buffers still hold another unit's rows) */
+                    uint32_t r[16];
+                    #pragma unroll
+                    for (int m = 0; m < 16; m++) r[m] = W[m / 5][m % 5];
+                    tmem_st16(dst, r);
+                    #pragma unroll
+                    for (int m = 0; m < 16; m++) r[m] = W[(m + 16) / 5][(m + 16) % 5];
+                    tmem_st16(dst + 16, r);
+                    #pragma unroll
+                    for (int m = 0; m < 13; m++) r[m] = W[(m + 32) / 5][(m + 32) % 5];
+                    r[13] = 0x3C003C00u;                          /* k = 90, 91: constant 1.0 (bias inputs) */
+                    r[14] = 0u; r[15] = 0u;
+                    tmem_st16(dst + 32, r);
+                } else {
+                    /* A1[b] still holds the operand of row n-2, and the slot -> column map never moves: only the two ring
+                     * slots refilled since then (Y rows n+7 and n+8) differ -- 10 of the 48 columns */
+                    constexpr int SA = (R + 7) % 9, SB = (R + 8) % 9;
+                    const uint32_t (&wa)[5] = W[SA];
+                    const uint32_t (&wb)[5] = W[SB];
+                    tmem_st4(dst + 5 * SA, wa[0], wa[1], wa[2], wa[3]);
+                    if (SB == SA + 1) {
+                        tmem_st2(dst + 5 * SA + 4, wa[4], wb[0]);
+                        tmem_st4(dst + 5 * SB + 1, wb[1], wb[2], wb[3], wb[4]);
+                    } else {
+                        tmem_st1(dst + 5 * SA + 4, wa[4]);
+                        tmem_st4(dst + 5 * SB, wb[0], wb[1], wb[2], wb[3]);
+                        tmem_st1(dst + 5 * SB + 4, wb[4]);
+                    }
+                }
                 tmem_wait_st();
                 tc_fence_before();
                 warp_arrive(BAR(A1_FULL) + 8u * b, lane);
@@ -504,7 +558,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         for (int g = 0; g < total; g += 2) {
             const uint32_t ph = (g >> 1) & 1;
             uint32_t v[64];
-            WAITS(2, 0, BAR(M1_DONE) + 8u * b, ph);
+            WAITS(3, 0, BAR(M1_DONE) + 8u * b, ph);
             tc_fence_after();
             tmem_ld32(d1, v);
             tmem_ld32(d1 + 32, v + 32);
@@ -513,7 +567,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);
             #pragma unroll
             for (int m = 0; m < 32; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
-            WAITP(1, BAR(M2_DONE) + 8u * b, ph ^ 1);                 /* MMA2 of the previous row of this parity has consumed A2[b] */
+            WAITS(6, 1, BAR(M2_DONE) + 8u * b, ph ^ 1);              /* MMA2 of the previous row of this parity has consumed A2[b] */
             tc_fence_after();
             tmem_st16(a2, v);
             tmem_st16(a2 + 16, v + 16);
@@ -542,7 +596,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 #pragma unroll
                 for (uint32_t b = 0; b < 2; b++) {
                     uint32_t v[32];
-                    WAITS(2, 0, BAR(M2_DONE + b), ph);
+                    WAITS(7, 0, BAR(M2_DONE + b), ph);
                     tc_fence_after();
                     tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
                     tmem_wait_ld();
@@ -559,7 +613,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 #pragma unroll
                 for (uint32_t b = 0; b < 2; b++) {
                     uint32_t v[32];
-                    WAITS(2, 0, BAR(M2_DONE + b), ph);
+                    WAITS(7, 0, BAR(M2_DONE + b), ph);
                     tc_fence_after();
                     tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
                     tmem_wait_ld();
@@ -620,12 +674,12 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 /* chroma of this pair was requested one set ago; request the next pair's now (a full set period to land) */
                 const float cb0 = ncb0, cr0 = ncr0, al0 = nal0, cb1 = ncb1, cr1 = ncr1, al1 = nal1;
                 if (pp + 1 < un.npairs) load_chroma(r + 2);
-                WAITS(2, 0, BAR(M3_DONE), sg & 1);
+                WAITS(10, 0, BAR(M3_DONE + (sg & 1)), (sg >> 1) & 1);
                 tc_fence_after();
-                tmem_ld16(lane_base + D3_COL, z);
+                tmem_ld16(lane_base + D3_COL + (sg & 1) * D3_STR, z);
                 tmem_wait_ld();
                 tc_fence_before();
-                warp_arrive(BAR(D3_EMPTY), lane);
+                warp_arrive(BAR(D3_EMPTY + (sg & 1)), lane);
                 float* P = sP + (sg & 1) * (10 * 128);
                 #pragma unroll
                 for (int m = 0; m < 10; m++) P[m * 128 + t] = __uint_as_float(z[m]);
@@ -722,12 +776,12 @@ int conv_tc_create(ConvTcState** out)
         }
     for (int n = 0; n < N2; n++)
         for (int k = 0; k < K2; k++) put(W_B2, n, k, K2, SRCNN_W2[k][n]);
-    /* conv II bias as a 32 x 16 operand for the constant-1 K-step: k = 0 hi part, k = 1 lo part */
+    /* conv II bias as a 32 x 16 operand for the constant-1 K-step (A = A1 columns 40..47): k = 10 hi part, k = 11 lo part */
     for (int n = 0; n < N2; n++) {
         const float b = SRCNN_B2[n];
         const float hi = __half2float(__float2half_rn(b));
-        put(W_B2B, n, 0, 16, hi);
-        put(W_B2B, n, 1, 16, b - hi);
+        put(W_B2B, n, KBIAS, 16, hi);
+        put(W_B2B, n, KBIAS + 1, 16, b - hi);
     }
     /* conv III, one 16 x 16 tile per K-step (rho, h): column n = 5*o + dx of output row r0+o takes conv II row r0-2+rho
      * with the tap dy+2 = rho - o (zero outside 0..4); k = channel 16*h + kk.  SRCNN_W3[tap = (dy+2)*5 + (dx+2)][ch]. */
