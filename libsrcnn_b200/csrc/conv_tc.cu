@@ -299,6 +299,9 @@ __device__ __forceinline__ int total_rows(const TcParams& p, const Span& sp)
 }
 
 
+/* FUSE: the gather group's store stage also does colour-out (optional, measured slower); the default instantiation
+ * carries none of that code */
+template <bool FUSE>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
 {
@@ -651,11 +654,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 pidx[d] = d * 128 + (cc < 0 ? 0 : (cc > 127 ? 127 : cc));
             }
             /* RGB (d = 3) rows are staged in shared memory and stored as words when the band's row segment is word-aligned */
-            const bool rgb_staged = p.rgb && p.d == 3 && (p.dw & 3) == 0 && ((uintptr_t)p.rgb & 3u) == 0;
+            const bool rgb_staged = FUSE && p.rgb && p.d == 3 && (p.dw & 3) == 0 && ((uintptr_t)p.rgb & 3u) == 0;
             const int nvalid = min(kBandCols, p.dw - un.band * kBandCols), nwords = (nvalid * 3) >> 2;
             float ncb0 = 0.f, ncr0 = 0.f, nal0 = 0.f, ncb1 = 0.f, ncr1 = 0.f, nal1 = 0.f;
             auto load_chroma = [&](int r) {
-                if (!(writer && p.rgb)) return;
+                if (!(FUSE && writer && p.rgb)) return;
                 const size_t ix = (size_t)(r - p.row0) * p.dw + c;
                 ncb0 = __ldg(p.cb + ix); ncr0 = __ldg(p.cr + ix);
                 if (p.d == 4) nal0 = __ldg(p.al + ix);
@@ -690,12 +693,12 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     for (int d = 0; d < 5; d++) { o0 += P[pidx[d]]; o1 += P[5 * 128 + pidx[d]]; }
                     o0 = fminf(fmaxf(o0, 0.f), 255.f);
                     o1 = fminf(fmaxf(o1, 0.f), 255.f);
-                    if (p.out) {
+                    if (!FUSE || p.out) {
                         float* dst = p.out + pix;
                         dst[0] = o0;
                         if (two) dst[p.dw] = o1;
                     }
-                    if (p.rgb) {
+                    if (FUSE && p.rgb) {
                         /* memcpy conv III -> Y, convertImgF32XtoImgU8, conv plane (src/libsrcnn.cpp:855-861, 889-915) */
                         auto emit = [&](float y, float cb, float cr, float al, size_t ix, unsigned char* stage) {
                             uint32_t R, G, B;
@@ -798,7 +801,8 @@ int conv_tc_create(ConvTcState** out)
     cudaError_t e = cudaMalloc(&st->d_wimg, WIMG_BYTES);
     if (e == cudaSuccess) e = cudaMemcpy(st->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(cBias3, &SRCNN_B3, sizeof(float));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) {
         void* fn = nullptr; cudaDriverEntryPointQueryResult q;
         e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
@@ -853,7 +857,8 @@ int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, u
     if (!d_prof) cudaMalloc(&d_prof, NWARPS * 4 * 8);
     p.prof = d_prof;
 #endif
-    conv_tc_kernel<<<grid, NWARPS * 32, SMEM_BYTES, s>>>(p, map);
+    if (p.rgb) conv_tc_kernel<true><<<grid, NWARPS * 32, SMEM_BYTES, s>>>(p, map);
+    else       conv_tc_kernel<false><<<grid, NWARPS * 32, SMEM_BYTES, s>>>(p, map);
 #ifdef SRCNN_PROF
     {
         cudaStreamSynchronize(s);
