@@ -309,7 +309,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* const sgen = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t sY = sbase + S_Y, sW = sbase + S_W, bar0 = sbase + S_BAR;
-    float* const sP = reinterpret_cast<float*>(sgen + S_P);
     unsigned char* const sOut = sgen + S_OUT;                          /* [set parity][row of the pair][124 px x 3 B] */
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -645,14 +644,16 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             const Unit un = unit_of(p, span, u);
             const int c0 = un.band * kBandCols - 2, c = c0 + t;
             const bool writer = (t >= 2 && t < 126 && c < p.dw);
-            int pidx[5];                        /* lane of column clamp(c + dx) -- conv III clamps its input plane */
+            uint32_t pa[5];                     /* shared address of the dx term: lane of column clamp(c + dx) -- conv III
+                                                   clamps its input plane -- in exchange buffer 0 */
             #pragma unroll
             for (int d = 0; d < 5; d++) {
                 int cc = c + d - 2;
                 cc = cc < 0 ? 0 : (cc > p.dw - 1 ? p.dw - 1 : cc);
                 cc -= c0;
-                pidx[d] = d * 128 + (cc < 0 ? 0 : (cc > 127 ? 127 : cc));
+                pa[d] = sbase + S_P + 4u * (uint32_t)(d * 128 + (cc < 0 ? 0 : (cc > 127 ? 127 : cc)));
             }
+            const uint32_t pst = sbase + S_P + 4u * (uint32_t)t;
             /* RGB (d = 3) rows are staged in shared memory and stored as words when the band's row segment is word-aligned */
             const bool rgb_staged = FUSE && p.rgb && p.d == 3 && (p.dw & 3) == 0 && ((uintptr_t)p.rgb & 3u) == 0;
             const int nvalid = min(kBandCols, p.dw - un.band * kBandCols), nwords = (nvalid * 3) >> 2;
@@ -668,12 +669,14 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 }
             };
             load_chroma(un.ra);
+            float* odst = (!FUSE || p.out) ? p.out + ((size_t)(un.ra - p.row0) * p.dw + c) : nullptr;   /* two rows further per set */
+            const size_t ostep = 2 * (size_t)p.dw;
             #pragma unroll 1
-            for (int pp = 0; pp < un.npairs; pp++, sg++) {
+            for (int pp = 0; pp < un.npairs; pp++, sg++, odst += ostep) {
                 uint32_t z[16];
                 const int r = un.ra + 2 * pp;
                 const bool two = r + 1 < un.rb;
-                const size_t pix = (size_t)(r - p.row0) * p.dw + c;
+                const size_t pix = FUSE ? (size_t)(r - p.row0) * p.dw + c : 0;
                 /* chroma of this pair was requested one set ago; request the next pair's now (a full set period to land) */
                 const float cb0 = ncb0, cr0 = ncr0, al0 = nal0, cb1 = ncb1, cr1 = ncr1, al1 = nal1;
                 if (pp + 1 < un.npairs) load_chroma(r + 2);
@@ -683,20 +686,26 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 tmem_wait_ld();
                 tc_fence_before();
                 warp_arrive(BAR(D3_EMPTY + (sg & 1)), lane);
-                float* P = sP + (sg & 1) * (10 * 128);
+                const uint32_t poff = (sg & 1) * (10 * 128 * 4);            /* exchange buffer of this set */
+                const uint32_t pdst = pst + poff;
                 #pragma unroll
-                for (int m = 0; m < 10; m++) P[m * 128 + t] = __uint_as_float(z[m]);
+                for (int m = 0; m < 10; m++)
+                    asm volatile("st.shared.b32 [%0], %1;" :: "r"(pdst + 512u * m), "r"(z[m]) : "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (writer) {
                     float o0 = cBias3, o1 = cBias3;
                     #pragma unroll
-                    for (int d = 0; d < 5; d++) { o0 += P[pidx[d]]; o1 += P[5 * 128 + pidx[d]]; }
+                    for (int d = 0; d < 5; d++) {
+                        float a0, a1;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a0) : "r"(pa[d] + poff) : "memory");
+                        asm volatile("ld.shared.f32 %0, [%1+2560];" : "=f"(a1) : "r"(pa[d] + poff) : "memory");
+                        o0 += a0; o1 += a1;
+                    }
                     o0 = fminf(fmaxf(o0, 0.f), 255.f);
                     o1 = fminf(fmaxf(o1, 0.f), 255.f);
                     if (!FUSE || p.out) {
-                        float* dst = p.out + pix;
-                        dst[0] = o0;
-                        if (two) dst[p.dw] = o1;
+                        odst[0] = o0;
+                        if (two) odst[p.dw] = o1;
                     }
                     if (FUSE && p.rgb) {
                         /* memcpy conv III -> Y, convertImgF32XtoImgU8, conv plane (src/libsrcnn.cpp:855-861, 889-915) */
