@@ -79,9 +79,16 @@ constexpr int W_TMA = W_CTL, W_MMA1 = W_CTL + 1, W_MMA2 = W_CTL + 2, W_MMA3 = W_
 
 /* barrier indices.  M?_DONE[b] fires when the MMAs of layer ? for a row with parity b have completed: it both frees the
  * A operand region for the producer group and publishes the accumulator to the consumer group. */
-enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + 2, D1_EMPTY = M1_DONE + 2,
-       A2_FULL = D1_EMPTY + 2, M2_DONE = A2_FULL + 2, D2_EMPTY = M2_DONE + 2,
-       A3_FULL = D2_EMPTY + 2, A3_EMPTY = A3_FULL + 4, M3_DONE = A3_EMPTY + 4, D3_EMPTY = M3_DONE + 2, NBAR = D3_EMPTY + 2 };
+/* SRCNN_MERGE_BAR: "operand written" and "accumulator drained" of conv I (and of conv II) arrive on ONE barrier of count 8
+ * (4 producer warps + 4 drainer warps; the drainers pre-arrive once for the first row of each parity), so the issuing lane
+ * -- the pipeline's critical thread -- probes one barrier per row instead of two. */
+#ifndef SRCNN_MERGE_BAR
+#define SRCNN_MERGE_BAR 1
+#endif
+enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + 2, D1_EMPTY_ = M1_DONE + 2,
+       A2_FULL = D1_EMPTY_ + 2, M2_DONE = A2_FULL + 2, D2_EMPTY_ = M2_DONE + 2,
+       A3_FULL = D2_EMPTY_ + 2, A3_EMPTY = A3_FULL + 4, M3_DONE = A3_EMPTY + 4, D3_EMPTY = M3_DONE + 2, NBAR = D3_EMPTY + 2,
+       D1_EMPTY = SRCNN_MERGE_BAR ? A1_FULL : D1_EMPTY_, D2_EMPTY = SRCNN_MERGE_BAR ? A2_FULL : D2_EMPTY_ };
 
 /* dynamic shared memory layout (offsets from a 1024-byte aligned base) */
 constexpr int S_Y = 0, S_W = NST * CH_BYTES, S_P = S_W + WIMG_BYTES, S_OUT = S_P + 2 * 10 * 128 * 4, S_BAR = S_OUT + 2 * 2 * 384,
@@ -324,8 +331,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     if (tid == 0) {
         for (int i = 0; i < NST; i++) { mbar_init(BAR(Y_FULL + i), 1); mbar_init(BAR(Y_EMPTY + i), 4); }
         for (int b = 0; b < 2; b++) {
-            mbar_init(BAR(A1_FULL + b), 4); mbar_init(BAR(M1_DONE + b), 1); mbar_init(BAR(D1_EMPTY + b), 4);
-            mbar_init(BAR(A2_FULL + b), 4); mbar_init(BAR(M2_DONE + b), 1); mbar_init(BAR(D2_EMPTY + b), 4);
+            mbar_init(BAR(A1_FULL + b), SRCNN_MERGE_BAR ? 8 : 4); mbar_init(BAR(M1_DONE + b), 1); mbar_init(BAR(D1_EMPTY_ + b), 4);
+            mbar_init(BAR(A2_FULL + b), SRCNN_MERGE_BAR ? 8 : 4); mbar_init(BAR(M2_DONE + b), 1); mbar_init(BAR(D2_EMPTY_ + b), 4);
         }
         for (int j = 0; j < 4; j++) { mbar_init(BAR(A3_FULL + j), 4); mbar_init(BAR(A3_EMPTY + j), 1); }
         for (int b = 0; b < 2; b++) { mbar_init(BAR(M3_DONE + b), 1); mbar_init(BAR(D3_EMPTY + b), 4); }
@@ -379,7 +386,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     #pragma unroll
                     for (uint32_t b = 0; b < 2; b++) {
                         WAITS(0, 0, BAR(A1_FULL + b), ph);
-                        WAITS(1, 1, BAR(D1_EMPTY + b), ph ^ 1);
+                        if (!SRCNN_MERGE_BAR) WAITS(1, 1, BAR(D1_EMPTY + b), ph ^ 1);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t db = db0 + R * (B1_BYTES >> 4);
@@ -404,7 +411,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 #pragma unroll
                 for (uint32_t b = 0; b < 2; b++) {
                     WAITS(4, 0, BAR(A2_FULL + b), ph);
-                    WAITS(5, 1, BAR(D2_EMPTY + b), ph ^ 1);
+                    if (!SRCNN_MERGE_BAR) WAITS(5, 1, BAR(D2_EMPTY + b), ph ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
                         #pragma unroll
@@ -556,6 +563,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         const uint32_t b = (uint32_t)(warp - W_E1) >> 2;
         const int total = total_rows(p, span);
         const uint32_t d1 = lane_base + D1_COL + b * D1_STR, a2 = lane_base + A2_COL + b * A2_STR;
+        if (SRCNN_MERGE_BAR && total > 0) warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);     /* D1[b] starts out drained */
         #pragma unroll 1
         for (int g = 0; g < total; g += 2) {
             const uint32_t ph = (g >> 1) & 1;
@@ -585,6 +593,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         reg_dec<64>();
 #endif
         uint32_t kg = 0;                                               /* global pair counter */
+        if (SRCNN_MERGE_BAR && span.nunits > 0) { warp_arrive(BAR(D2_EMPTY + 0), lane); warp_arrive(BAR(D2_EMPTY + 1), lane); }   /* D2 starts out drained */
         for (int u = 0; u < span.nunits; u++) {
             const Unit un = unit_of(p, span, u);
             #pragma unroll 1

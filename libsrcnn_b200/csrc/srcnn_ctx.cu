@@ -138,6 +138,7 @@ struct srcnn_b200_ctx {
     bool chain_tensor = false;      /* step-scale chains: tensor kernel also for the intermediate passes */
     bool timing = false;
     cudaEvent_t ev[8] = {};
+    int ev_alias[8] = { 0, 1, 2, 3, 4, 5, 6, 7 };   /* event that stands for stage boundary i (Stamp) */
     cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
     float ms[7] = {};
     unsigned long long launches = 0;
@@ -267,10 +268,14 @@ int make_plan(unsigned w, unsigned h, unsigned d, float multiply, int filter, un
     return 0;
 }
 
+/* per-kernel CUDA events of one pass (only while timing is on).  skip(n) marks n stage boundaries that coincide with the
+ * previous one (stages folded into one kernel): no event is recorded for them -- every record between two kernels costs
+ * GPU idle time -- and collect_timing reports 0 for those stages. */
 struct Stamp {
     srcnn_b200_ctx* c; int i = 0;
-    explicit Stamp(srcnn_b200_ctx* c_) : c(c_) { mark(); }
-    void mark() { if (c->timing && i < 8) cudaEventRecord(c->ev[i], c->stream); i++; }
+    explicit Stamp(srcnn_b200_ctx* c_) : c(c_) { c->ev_alias[0] = 0; mark(); }
+    void mark() { if (c->timing && i < 8) { cudaEventRecord(c->ev[i], c->stream); c->ev_alias[i] = i; } i++; }
+    void skip(int n) { for (; n > 0 && i < 8; n--, i++) c->ev_alias[i] = c->ev_alias[i - 1]; }
 };
 
 /* d_src_base points at source row `src_base_row` (device; kWholeImage = row 0, kStripRows = row p.s0);
@@ -318,7 +323,7 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
     }
     if (fused) {
         ctx->launches++;
-        st.mark(); st.mark(); st.mark(); st.mark();
+        st.mark(); st.skip(3);
         ctx->last_has_y32 = y32;
     } else {
         CK(ctx->planes_src.ensure(ps_src * p.d * sizeof(float)));
@@ -402,7 +407,8 @@ int collect_timing(srcnn_b200_ctx* ctx)
     if (!ctx->timing) return 0;
     for (int i = 0; i < 6; i++) {
         float v = 0.f;
-        if (cudaEventElapsedTime(&v, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) v = -1.f;
+        const int a = ctx->ev_alias[i], b = ctx->ev_alias[i + 1];
+        if (a != b && cudaEventElapsedTime(&v, ctx->ev[a], ctx->ev[b]) != cudaSuccess) v = -1.f;
         ctx->ms[i] = v;
     }
     float v = 0.f;
