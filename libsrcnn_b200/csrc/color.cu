@@ -139,4 +139,141 @@ void launch_color_out(const float* yp, const float* cb, const float* cr, const f
 #undef SRCNN_CO
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Colour-out with the chroma / alpha resampling folded in (magnification where the bilinear / box tables are "pow2pair",
+ * i.e. x2: weights 0.25 / 0.75 / 1 / 0).  Cb, Cr (, A) arrive at SOURCE resolution (written by the fused front end) and are
+ * resampled here exactly as FRAWResizeEngine::scale does it -- vertical pass first, one rounding to FP32 after each pass
+ * (src/frawscale.cpp:238-278) -- with fmaf(wA, vA, wB * vB): the product with the 0-or-power-of-two weight is exact, so
+ * the fused multiply-add rounds the exact two-tap sum once, which is what the reference's double accumulation + cast
+ * yields for these operands (prep.cu header).  A CTA owns 1024 pixels of one output row: it resamples the source columns
+ * they touch vertically into shared memory (coalesced loads, each column once), then every thread mixes two of those per
+ * pixel with its packed table entries (one 16-byte load per pixel) and runs the colour-out arithmetic for 4 pixels.
+ * Saves the 4 B/px/plane write + read of the output-size chroma planes (66 MB of 4K RGB traffic each way). */
+__device__ __forceinline__ float mix2f(float wA, float vA, float wB, float vB) { return __fmaf_rn(wA, vA, __fmul_rn(wB, vB)); }
+
+constexpr int kUpBlockPx = 1024;              /* output pixels of one row per CTA (256 threads x 4) */
+constexpr int kUpIters = 3;                   /* staging passes of 256 columns */
+constexpr int kUpMaxCols = 256 * kUpIters;    /* source columns a CTA may need: magnification >= ~1.35 (x2: 515) */
+
+/* pack2 entry of a two-tap table (built on the host, srcnn_ctx.cu): x = left + (index of tap A), y = wA bits, z = wB bits,
+ * w = left + (index of tap B); B is the tap whose weight is 0 or a power of two */
+constexpr int kUpRowsMax = 16;                /* consecutive output rows per CTA (the horizontal table entries stay in registers);
+                                                 fewer for small images so that the grid still fills the SMs */
+
+template <int D, bool CONV>
+__global__ void __launch_bounds__(256)
+color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc, size_t cstride, unsigned w, unsigned src_row0,
+                    const int4* __restrict__ vpack, const int4* __restrict__ hpack,
+                    unsigned ow, unsigned row0, unsigned nrows, unsigned rpc, uint8_t* __restrict__ out, uint8_t* __restrict__ conv)
+{
+    constexpr int NC = D - 1;
+    __shared__ float tS[2][NC][kUpMaxCols];       /* the intermediate (vertically resampled) plane, this CTA's columns; by row parity */
+    const unsigned xb = blockIdx.x * kUpBlockPx;
+    const unsigned xe = min(xb + kUpBlockPx, ow) - 1;                 /* last pixel of this CTA */
+    const int4 hb = __ldg(hpack + xb), he = __ldg(hpack + xe);
+    const int c_lo = min(hb.x, hb.w), ncols = max(he.x, he.w) - c_lo + 1;   /* source columns [c_lo, c_lo + ncols) */
+    const unsigned x0 = xb + threadIdx.x * 4;
+    const bool active = x0 < ow;
+    int ia[4], ib[4]; float hA[4], hB[4];
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int4 hp = active ? __ldg(hpack + x0 + i) : make_int4(c_lo, 0, 0, c_lo);
+        ia[i] = hp.x - c_lo; ib[i] = hp.w - c_lo; hA[i] = __int_as_float(hp.y); hB[i] = __int_as_float(hp.z);
+    }
+    const unsigned ry0 = blockIdx.y * rpc, ry1 = min(ry0 + rpc, nrows);
+    /* software pipeline over the rows: the source samples (and Y') of row r+1 are requested before row r is computed, so
+     * their latency hides behind the colour arithmetic -- one barrier per row, the staging buffer alternates by row parity */
+    float pa[kUpIters][NC], pb[kUpIters][NC], pvA = 0.f, pvB = 0.f;
+    float4 py = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto prefetch = [&](unsigned ry) {
+        const int4 vp = __ldg(vpack + row0 + ry);                     /* vertical taps of image row row0 + ry */
+        pvA = __int_as_float(vp.y); pvB = __int_as_float(vp.z);
+        const float* rA = csrc + (size_t)(vp.x - (int)src_row0) * w + c_lo;
+        const float* rB = csrc + (size_t)(vp.w - (int)src_row0) * w + c_lo;
+        #pragma unroll
+        for (int it = 0; it < kUpIters; it++) {
+            const int j = threadIdx.x + 256 * it;
+            if (j < ncols) {
+                #pragma unroll
+                for (int k = 0; k < NC; k++) { pa[it][k] = __ldg(rA + k * cstride + j); pb[it][k] = __ldg(rB + k * cstride + j); }
+            }
+        }
+        if (active) py = __ldg(reinterpret_cast<const float4*>(yp + (size_t)ry * ow + x0));
+    };
+    if (ry0 < ry1) prefetch(ry0);
+    for (unsigned ry = ry0; ry < ry1; ry++) {
+        float (*t)[kUpMaxCols] = tS[ry & 1];
+        #pragma unroll
+        for (int it = 0; it < kUpIters; it++) {
+            const int j = threadIdx.x + 256 * it;
+            if (j < ncols) {
+                #pragma unroll
+                for (int k = 0; k < NC; k++) t[k][j] = mix2f(pvA, pa[it][k], pvB, pb[it][k]);
+            }
+        }
+        const float4 y4 = py;
+        __syncthreads();                /* (the other parity's buffer was last read before the previous row's barrier) */
+        if (ry + 1 < ry1) prefetch(ry + 1);
+        if (!active) continue;
+        const size_t i0 = (size_t)ry * ow + x0;
+        const float Y[4] = { y4.x, y4.y, y4.z, y4.w };
+        uint32_t bytes[4 * D];
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float c[NC];
+            #pragma unroll
+            for (int k = 0; k < NC; k++) c[k] = mix2f(hA[i], t[k][ia[i]], hB[i], t[k][ib[i]]);
+            rgb_of(Y[i], c[0], c[1], bytes[i * D], bytes[i * D + 1], bytes[i * D + 2]);
+            if (D == 4) bytes[i * D + 3] = to_u8(c[NC - 1]);
+        }
+        uint32_t wds[D];
+        #pragma unroll
+        for (int wi = 0; wi < D; wi++)
+            wds[wi] = bytes[wi * 4] | (bytes[wi * 4 + 1] << 8) | (bytes[wi * 4 + 2] << 16) | (bytes[wi * 4 + 3] << 24);
+        const size_t qi = i0 / 4;
+        if (D == 4) {
+            reinterpret_cast<uint4*>(out)[qi] = make_uint4(wds[0], wds[1], wds[2], wds[D - 1]);
+        } else {
+            uint32_t* p = reinterpret_cast<uint32_t*>(out) + qi * 3;
+            p[0] = wds[0]; p[1] = wds[1]; p[2] = wds[2];
+        }
+        if (CONV)
+            reinterpret_cast<uint32_t*>(conv)[qi] = __float2uint_rz(Y[0]) | (__float2uint_rz(Y[1]) << 8) |
+                                                    (__float2uint_rz(Y[2]) << 16) | (__float2uint_rz(Y[3]) << 24);
+    }
+}
+
+/* host-side: the source columns one CTA (kUpBlockPx output pixels) reads fit its shared-memory row, and lefts are monotonic */
+bool color_out_up_quads_ok(const int* h_hcl, unsigned ow)
+{
+    if (ow % 4) return false;
+    for (unsigned x = 0; x < ow; x += kUpBlockPx) {
+        const unsigned e = (x + kUpBlockPx < ow ? x + kUpBlockPx : ow) - 1;
+        if (h_hcl[e] + 1 - h_hcl[x] + 1 > kUpMaxCols) return false;
+    }
+    for (unsigned x = 1; x < ow; x++) if (h_hcl[x] < h_hcl[x - 1]) return false;
+    return true;
+}
+
+bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, unsigned w, unsigned src_row0,
+                         const AxisTableDev& vc, const AxisTableDev& hc, unsigned ow, unsigned row0, unsigned row1, unsigned d,
+                         uint8_t* out, uint8_t* conv, cudaStream_t s)
+{
+    auto al = [](const void* p, unsigned a) { return ((uintptr_t)p % a) == 0; };
+    if (!vc.pack2 || !hc.pack2 || (ow % 4) || row1 <= row0) return false;
+    if (!al(yp, 16) || !al(out, d == 4 ? 16 : 4) || (conv && !al(conv, 4))) return false;
+    const unsigned gx = (ow + kUpBlockPx - 1) / kUpBlockPx, nrows = row1 - row0;
+    unsigned rpc = (unsigned)(((size_t)gx * nrows) / (148u * 8u));          /* aim at >= 8 CTAs per SM */
+    rpc = rpc < 2 ? 2 : (rpc > (unsigned)kUpRowsMax ? (unsigned)kUpRowsMax : rpc);
+    dim3 grid(gx, (nrows + rpc - 1) / rpc);
+    if (grid.y > 65535u) return false;
+#define SRCNN_COU(D_, C_) color_out_up_kernel<D_, C_><<<grid, 256, 0, s>>>(yp, csrc, cstride, w, src_row0, \
+        reinterpret_cast<const int4*>(vc.pack2), reinterpret_cast<const int4*>(hc.pack2), ow, row0, nrows, rpc, out, conv)
+    if (d == 4) { if (conv) SRCNN_COU(4, true); else SRCNN_COU(4, false); }
+    else        { if (conv) SRCNN_COU(3, true); else SRCNN_COU(3, false); }
+#undef SRCNN_COU
+    return true;
+}
+
 } // namespace srcnn

@@ -24,6 +24,7 @@ struct AxisTableDev {
     int           cwin;
     int           exact29;  /* all weights have <= 29 significant bits: fma == mul, add */
     int           pow2pair; /* cwin == 2, both weights exact in FP32, one of each pair 0 or a power of two (prep.cu) */
+    const void*   pack2;    /* pow2pair only: [dst] int4 { left + idx(tap A), bits(wA), bits(wB), left + idx(tap B) } (color.cu) */
 };
 
 /* geometry of the FP16 conv-input plane consumed by the tensor-core kernel (see DESIGN.md "Y16 plane") */
@@ -63,7 +64,12 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
                 unsigned e0, unsigned e1, float* planes, size_t plane_stride, bool write_y32,
                 __half* y16, Y16Geom g, unsigned strip_row0,
                 const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc,
-                const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, cudaStream_t s);
+                const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, cudaStream_t s,
+                float* csrc = nullptr, size_t csrc_stride = 0);
+/* csrc (optional, honoured only when the chroma tables are "pow2pair"): Cb / Cr / A are NOT resampled; their colour-converted
+ * FP32 samples are stored at source resolution, plane k at csrc + k * csrc_stride, row 0 = source row src_row0, pitch w,
+ * for launch_color_out_up to resample.  prep_chroma_handover() tells whether a set of tables takes that route. */
+bool prep_chroma_handover(const AxisTableDev& vc, const AxisTableDev& hc);
 /* host-side applicability test of launch_prep for a set of tables */
 bool prep_supported(const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc);
 
@@ -97,6 +103,14 @@ int  launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, 
 const char* conv_tc_error(const ConvTcState* st);
 
 /* colour-out: Y' + Cb/Cr/(A) -> interleaved u8 (+ optional u8 conv plane); all arrays are `npix` long views */
+/* colour-out with the x2 chroma / alpha resampling folded in (color.cu): csrc = source-resolution FP32 Cb, Cr (, A) planes
+ * written by launch_prep (plane k at csrc + k * cstride, row 0 = source row src_row0, pitch w); yp / out / conv = rows
+ * [row0,row1) of the strip.  Returns false (nothing launched) if the geometry is not covered. */
+bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, unsigned w, unsigned src_row0,
+                         const AxisTableDev& vc, const AxisTableDev& hc, unsigned ow, unsigned row0, unsigned row1, unsigned d,
+                         uint8_t* out, uint8_t* conv, cudaStream_t s);
+/* host-side: the source columns any CTA of that kernel reads fit its shared-memory row (h_hcl = compact lefts of the table) */
+bool color_out_up_quads_ok(const int* h_hcl, unsigned ow);
 void launch_color_out(const float* yprime, const float* cb, const float* cr, const float* a, size_t npix,
                       unsigned d, uint8_t* out, uint8_t* conv, cudaStream_t s);
 

@@ -55,6 +55,10 @@ struct PrepParams {
     const int *vyl, *vcl, *hyl, *hcl;     /* compact lefts   */
     const double *vyw, *vcw, *hyw, *hcw;  /* compact weights */
     int SR, SC;                 /* shared-memory capacity of the source footprint (rows, columns) */
+    /* chroma hand-over at SOURCE resolution (chroma mode 2 only, may be NULL): instead of resampling Cb / Cr / A here, the
+     * colour-converted FP32 samples of the footprint are written to csrc[plane][(row - src_row0) * w + col] and the x2
+     * colour-out kernel (color.cu: color_out_up_kernel) resamples them on the fly -- 4 x less chroma traffic */
+    float* csrc; size_t csrc_stride;
 };
 
 __device__ __forceinline__ void ycbcr_of(float r, float g, float b, float& y, float& cb, float& cr)
@@ -247,7 +251,12 @@ prep_kernel(const PrepParams p)
                     ycbcr_of((float)v[k][0], (float)v[k][1], (float)v[k][2], y, cb_, cr);
                     if (c < nc) {
                         s[c] = (double)y;
-                        if (C32) {
+                        if (C32 && p.csrc) {
+                            /* neighbouring tiles' footprints overlap: they store identical values (benign) */
+                            float* q = p.csrc + (size_t)(rlo + r - (int)p.src_row0) * p.w + (size_t)(clo + c);
+                            q[0] = cb_; q[p.csrc_stride] = cr;
+                            if (NC == 3) q[2 * p.csrc_stride] = (float)v[k][D - 1];
+                        } else if (C32) {
                             float* q = Sc + ((size_t)r * SC + c) * NC;
                             if (NC == 2) *reinterpret_cast<float2*>(q) = make_float2(cb_, cr);
                             else { q[0] = cb_; q[1] = cr; q[2] = (float)v[k][D - 1]; }
@@ -324,7 +333,9 @@ prep_kernel(const PrepParams p)
     }
 
     /* 3. planes 1 .. D-1 (Cb, Cr, A): bilinear / box tables */
-    if (C32) {
+    if (C32 && p.csrc) {
+        /* handed over at source resolution (colour-in above) */
+    } else if (C32) {
         float* Tc = reinterpret_cast<float*>(T);
         vpass_c32<NC, SC>(Sc, Tc, nc, ny, s_vl[1], s_vwc, warp, lane);
         __syncthreads();
@@ -367,8 +378,9 @@ prep_kernel(const PrepParams p)
 }
 
 /* dynamic shared memory of one CTA (bytes) */
-inline size_t prep_smem(int d, int cm, int SR, int SC)
+inline size_t prep_smem(int d, int cm, int SR, int SC, bool csrc)
 {
+    if (cm == 2 && csrc) return ((size_t)SR + TH) * SC * sizeof(double);
     if (cm == 2) return ((size_t)SR + (d == 4 ? 2 : 1) * TH) * SC * sizeof(double) + (size_t)SR * SC * (d - 1) * sizeof(float);
     return ((size_t)d * SR + TH) * SC * sizeof(double);
 }
@@ -383,7 +395,7 @@ int launch_one(const PrepParams& p, dim3 grid, cudaStream_t s)
         }
         configured = true;
     }
-    prep_kernel<D, WY, WC, CM, SC><<<grid, NT, prep_smem(D, CM, p.SR, SC), s>>>(p);
+    prep_kernel<D, WY, WC, CM, SC><<<grid, NT, prep_smem(D, CM, p.SR, SC, p.csrc != nullptr), s>>>(p);
     return 1;
 }
 
@@ -434,6 +446,11 @@ int max_footprint(const int* ly, int wy, const int* lc, int wc, unsigned d0, uns
 
 } // namespace
 
+bool prep_chroma_handover(const AxisTableDev& vc, const AxisTableDev& hc)
+{
+    return vc.pow2pair && hc.pow2pair && !getenv_flag("SRCNN_B200_PREP_F64");
+}
+
 bool prep_supported(const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc)
 {
     if (!vy.cleft || !vc.cleft || !hy.cleft || !hc.cleft) return false;
@@ -445,7 +462,8 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
                 unsigned e0, unsigned e1, float* planes, size_t plane_stride, bool write_y32,
                 __half* y16, Y16Geom g, unsigned strip_row0,
                 const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc,
-                const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, cudaStream_t s)
+                const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, cudaStream_t s,
+                float* csrc, size_t csrc_stride)
 {
     if (!prep_supported(vy, vc, hy, hc) || (d != 3 && d != 4)) return 0;
     PrepParams p;
@@ -458,7 +476,9 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
     p.SC = max_footprint(h_hyl, hy.cwin, h_hcl, hc.cwin, 0, ow, TW);
     /* chroma arithmetic: 2 = FP32 two-tap (pow2pair tables), 1 = FP64 fused multiply-add (exact29), 0 = FP64 mul + add */
     const int cm = (vc.pow2pair && hc.pow2pair && !getenv_flag("SRCNN_B200_PREP_F64")) ? 2 : (vc.exact29 && hc.exact29) ? 1 : 0;
-    if (prep_smem((int)d, cm, p.SR, 104) > 160 * 1024) return 0;
+    if (cm != 2) csrc = nullptr;
+    p.csrc = csrc; p.csrc_stride = csrc_stride;
+    if (prep_smem((int)d, cm, p.SR, 104, csrc != nullptr) > 160 * 1024) return 0;
     if ((size_t)oh * 8 >= (size_t)INT_MAX || (size_t)ow * 8 >= (size_t)INT_MAX) return 0;
     dim3 grid((ow + TW - 1) / TW, (e1 - e0 + TH - 1) / TH);
     if (grid.y > 65535u) return 0;

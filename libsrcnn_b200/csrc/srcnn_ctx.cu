@@ -112,6 +112,7 @@ struct TableDev {
     AxisTable host;
     void* dev = nullptr;
     AxisTableDev view{};
+    bool quads_ok = false;      /* compact form: 4 adjacent destination samples read <= 4 adjacent source samples (color.cu) */
 };
 
 /* geometry of one pass restricted to a row strip */
@@ -130,7 +131,7 @@ struct Plan {
 struct srcnn_b200_ctx {
     int device = 0, num_sms = 0;
     cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
-    DevBuf src8[2], planes_src, tmp, planes_dst, y16, yprime, out8[2], conv8[2], chain[2];
+    DevBuf src8[2], planes_src, tmp, planes_dst, y16, yprime, out8[2], conv8[2], chain[2], chroma_src;
     PinBuf pin_in[2], pin_out[2], pin_conv[2];
     std::map<std::tuple<int, unsigned, unsigned>, TableDev*> tables;
     ConvTcState* tc = nullptr;
@@ -151,6 +152,8 @@ struct srcnn_b200_ctx {
     bool fuse_front = true;                   /* one-kernel front end (SRCNN_B200_FUSE=0: the separate kernels)       */
     bool keep_planes = false;                 /* also write the FP32 interpolated Y plane in tensor mode (getters)    */
     bool last_has_y32 = false;
+    bool last_has_chroma = true;              /* output-size Cb / Cr / A planes of the last pass exist (getters 1-3)   */
+    bool chroma_up = true;                    /* x2: chroma resampled inside colour-out (SRCNN_B200_CHROMA_UP=0: off)  */
     bool last_has_yp = true;                  /* the FP32 network output Y' of the last pass exists (plane getter 4)  */
     bool fuse_color = false;                  /* tensor mode: colour-out inside the conv kernel's store stage (SRCNN_B200_FUSE_COLOR=1).
                                                * Off by default: measured 0.202 ms fused vs 0.155 + 0.023 ms separate per 4K frame --
@@ -200,7 +203,9 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     const size_t ints = (size_t)dst * sizeof(int);
     const size_t ints_al = (4 * ints + 15) / 16 * 16;
     const size_t wbytes = h.w.size() * sizeof(double), cbytes = h.cw.size() * sizeof(double);
-    const size_t bytes = ints_al + 2 * wbytes + cbytes;
+    const size_t pbytes = (h.compact && h.pow2pair) ? (size_t)dst * 16 : 0;       /* pack2 (color.cu) */
+    const size_t poff = (ints_al + 2 * wbytes + cbytes + 15) / 16 * 16;
+    const size_t bytes = poff + pbytes;
     std::vector<unsigned char> img(bytes, 0);
     int* L = reinterpret_cast<int*>(img.data());
     int* C = L + dst;
@@ -213,6 +218,17 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     if (h.compact) {
         memcpy(C + 2 * dst, h.cleft.data(), ints);
         memcpy(img.data() + ints_al + 2 * wbytes, h.cw.data(), cbytes);
+    }
+    if (pbytes) {
+        int* P = reinterpret_cast<int*>(img.data() + poff);
+        for (unsigned u = 0; u < dst; u++) {
+            const float w0 = (float)h.cw[2 * (size_t)u], w1 = (float)h.cw[2 * (size_t)u + 1];
+            uint32_t b1; memcpy(&b1, &w1, 4);
+            const bool swap = (b1 & 0x7FFFFFu) != 0;             /* tap 1 is the general one -> A = tap 1, B = tap 0 */
+            const float wA = swap ? w1 : w0, wB = swap ? w0 : w1;
+            P[4 * u] = h.cleft[u] + (swap ? 1 : 0); memcpy(&P[4 * u + 1], &wA, 4); memcpy(&P[4 * u + 2], &wB, 4);
+            P[4 * u + 3] = h.cleft[u] + (swap ? 0 : 1);
+        }
     }
     cudaError_t e = cudaMalloc(&t->dev, bytes);
     if (e != cudaSuccess) { delete t; return fail_cuda(ctx, e, "cudaMalloc(table)"); }
@@ -231,6 +247,8 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     t->view.cwin  = h.cwin;
     t->view.exact29 = h.exact29 ? 1 : 0;
     t->view.pow2pair = h.pow2pair ? 1 : 0;
+    t->view.pack2 = pbytes ? base + poff : nullptr;
+    t->quads_ok = h.compact && h.cwin == 2 && color_out_up_quads_ok(h.cleft.data(), dst);
     ctx->tables[key] = t;
     *out = t;
     return 0;
@@ -314,13 +332,23 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
     Stamp st(ctx);
     /* 1.-4. front end.  Preferred: ONE kernel (colour-in + both resampling passes + conv-input pack, prep.cu) */
     const bool y32 = !tensor || ctx->keep_planes;
-    bool fused = false;
+    bool fused = false, chroma_up = false;
+    const size_t ps_csrc = al((size_t)srows * p.w);
     if (ctx->fuse_front && !p.hfirst && p.need_h && p.need_v && prep_supported(vy->view, vc->view, hy->view, hc->view)) {
+        /* x2-type magnification: Cb / Cr / A stay at source resolution and are resampled inside colour-out (the output-size
+         * chroma planes then never exist -- unless the plane getters were asked to keep them) */
+        chroma_up = ctx->chroma_up && !ctx->keep_planes && !(tensor && ctx->fuse_color) && prep_chroma_handover(vc->view, hc->view) && (p.ow % 4) == 0 &&
+                    hc->quads_ok && ((uintptr_t)d_out % (p.d == 4 ? 16 : 4)) == 0 &&
+                    (!d_conv || ((uintptr_t)d_conv % 4) == 0);
+        if (chroma_up) CK(ctx->chroma_src.ensure(ps_csrc * (p.d - 1) * sizeof(float)));
         fused = launch_prep(d_src, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, P_dst, ps_dst, y32,
                             tensor ? static_cast<__half*>(ctx->y16.p) : nullptr, g, p.r0,
                             vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
-                            hy->host.cleft.data(), hc->host.cleft.data(), s) != 0;
+                            hy->host.cleft.data(), hc->host.cleft.data(), s,
+                            chroma_up ? static_cast<float*>(ctx->chroma_src.p) : nullptr, ps_csrc) != 0;
+        if (!fused) chroma_up = false;
     }
+    ctx->last_has_chroma = !chroma_up;
     if (fused) {
         ctx->launches++;
         st.mark(); st.skip(3);
@@ -392,7 +420,14 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
     }
     st.mark();
     /* 6. colour-out (+ conv plane) for the strip rows, unless the conv kernel already stored them */
-    if (!fuse_out) {
+    if (!fuse_out && chroma_up) {
+        if (!launch_color_out_up(Yp, static_cast<const float*>(ctx->chroma_src.p), ps_csrc, p.w, p.s0, vc->view, hc->view,
+                                 p.ow, p.r0, p.r1, p.d, d_out, d_conv, s)) {
+            ctx->err = "colour-out (x2 chroma path): geometry not covered";
+            return SRCNN_B200_ECUDA;
+        }
+        ctx->launches++;
+    } else if (!fuse_out) {
         launch_color_out(Yp, P_dst + ps_dst + off, P_dst + 2 * ps_dst + off, p.d == 4 ? P_dst + 3 * ps_dst + off : nullptr,
                          (size_t)orows * p.ow, p.d, d_out, d_conv, s); ctx->launches++;
     }
@@ -452,6 +487,7 @@ int srcnn_b200_create(int device, srcnn_b200_ctx** out)
     if (const char* e = getenv("SRCNN_B200_STAGE")) ctx->stage_pageable = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_FUSE")) ctx->fuse_front = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_FUSE_COLOR")) ctx->fuse_color = atoi(e) != 0;
+    if (const char* e = getenv("SRCNN_B200_CHROMA_UP")) ctx->chroma_up = atoi(e) != 0;
     {
         unsigned nt = std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2));
         if (const char* e = getenv("SRCNN_B200_COPY_THREADS")) nt = (unsigned)std::max(1, atoi(e));
@@ -490,6 +526,7 @@ void srcnn_b200_destroy(srcnn_b200_ctx* ctx)
         if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
         if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
     }
+    ctx->chroma_src.release();
     ctx->planes_src.release(); ctx->tmp.release(); ctx->planes_dst.release(); ctx->y16.release(); ctx->yprime.release();
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
@@ -798,6 +835,7 @@ int srcnn_b200_get_plane(srcnn_b200_ctx* ctx, int which, float* host, size_t cap
     if (which == 3 && p.d != 4) return SRCNN_B200_EINVAL;
     if (which == 0 && !ctx->last_has_y32) return SRCNN_B200_EINVAL;      /* see srcnn_b200_set_keep_planes */
     const float* srcp; unsigned r0, nr;
+    if (which >= 1 && which <= 3 && !ctx->last_has_chroma) return SRCNN_B200_EINVAL;   /* see srcnn_b200_set_keep_planes */
     if (which == 4 && !ctx->last_has_yp) return SRCNN_B200_EINVAL;       /* see srcnn_b200_set_keep_planes */
     if (which == 4) { srcp = static_cast<const float*>(ctx->yprime.p); r0 = p.r0; nr = p.r1 - p.r0; }
     else { srcp = static_cast<const float*>(ctx->planes_dst.p) + (size_t)which * ctx->last_plane_stride; r0 = p.e0; nr = p.e1 - p.e0; }

@@ -168,6 +168,7 @@ def test_chroma_planes_fp32_path_bit_exact(ctx, d, hw, filt):
     fc = S.NEAREST if filt == S.NEAREST else S.BILINEAR
     want = [o.resize(planes[k], 2 * w, 2 * h, fc) for k in range(1, d)]
     ctx.set_conv_mode(S.CONV_TENSOR)
+    ctx.set_keep_planes(True)        # otherwise the output-size chroma planes are never materialised (x2 colour-out path)
     got = {}
     for mode in ("f32", "f64"):
         if mode == "f64":
@@ -185,6 +186,40 @@ def test_chroma_planes_fp32_path_bit_exact(ctx, d, hw, filt):
     ctx.pass_host(img, 2.0, filt, rows=(r0, r1))
     a, pl = ctx.get_plane(1, (2 * h, 2 * w))
     assert np.array_equal(pl, want[0][a:a + pl.shape[0]])
+    ctx.set_keep_planes(False)
+
+
+@pytest.mark.parametrize("d,hw,filt", [(3, (62, 84), S.BICUBIC), (4, (47, 130), S.LANCZOS3), (3, (9, 6), S.BILINEAR),
+                                       (4, (33, 64), S.NEAREST), (3, (120, 250), S.BSPLINE)])
+def test_chroma_resampled_inside_colour_out(d, hw, filt):
+    """x2 with an output width that is a multiple of 4: Cb / Cr / A are handed over at source resolution and resampled
+    inside colour-out (color_out_up_kernel).  Exact mode must stay bit-identical to the oracle, equal to the route through
+    output-size planes (SRCNN_B200_CHROMA_UP=0), for whole images and strips; the chroma plane getters report that the
+    planes do not exist."""
+    import os
+    h, w = hw
+    img = O.synth("uniform", h, w, d, 91)
+    rc, want, want_conv = O.best().process(img, 2.0, filt, False, True)
+    assert rc == 0
+    outs = {}
+    for up in ("1", "0"):
+        os.environ["SRCNN_B200_CHROMA_UP"] = up
+        try:
+            c = S.Context(0, S.CONV_EXACT)
+        finally:
+            os.environ.pop("SRCNN_B200_CHROMA_UP", None)
+        out, conv = c.pass_host(img, 2.0, filt, True)
+        assert np.array_equal(out.reshape(-1), want) and np.array_equal(conv.reshape(-1), want_conv), "CHROMA_UP=" + up
+        if up == "1":
+            with pytest.raises(S.SrcnnError):
+                c.get_plane(1, (2 * h, 2 * w))
+        r0, r1 = (2 * h) // 3, (2 * h) // 3 + max(1, h // 2)
+        so, sc = c.pass_host(img, 2.0, filt, True, rows=(r0, r1))
+        assert np.array_equal(so, out[r0:r1]) and np.array_equal(sc, conv[r0:r1])
+        c.set_conv_mode(S.CONV_TENSOR)
+        outs[up], _ = c.pass_host(img, 2.0, filt, False)
+        c.close()
+    assert np.array_equal(outs["1"], outs["0"])          # the conv kernel is the same; only the chroma route differs
 
 
 def test_dropin_cpp_api_matches_oracle():
