@@ -152,15 +152,15 @@ void launch_color_out(const float* yp, const float* cb, const float* cr, const f
  * Saves the 4 B/px/plane write + read of the output-size chroma planes (66 MB of 4K RGB traffic each way). */
 __device__ __forceinline__ float mix2f(float wA, float vA, float wB, float vB) { return __fmaf_rn(wA, vA, __fmul_rn(wB, vB)); }
 
-constexpr int kUpBlockPx = 1024;              /* output pixels of one row per CTA (256 threads x 4) */
-constexpr int kUpIters = 3;                   /* staging passes of 256 columns */
-constexpr int kUpMaxCols = 256 * kUpIters;    /* source columns a CTA may need: magnification >= ~1.35 (x2: 515) */
-
-/* pack2 entry of a two-tap table (built on the host, srcnn_ctx.cu): x = left + (index of tap A), y = wA bits, z = wB bits,
- * w = left + (index of tap B); B is the tap whose weight is 0 or a power of two */
+constexpr int kUpBlockPx = 1024;              /* output pixels of one row per CTA (8 warps x 32 threads x 4 pixels) */
+constexpr int kUpWarpPx = 128;                /* ... per warp */
+constexpr int kUpIters = 3;                   /* staging passes of 32 columns */
+constexpr int kUpMaxCols = 32 * kUpIters;     /* source columns a warp may need: magnification >= ~1.37 (x2: 66) */
 constexpr int kUpRowsMax = 16;                /* consecutive output rows per CTA (the horizontal table entries stay in registers);
                                                  fewer for small images so that the grid still fills the SMs */
 
+/* pack2 entry of a two-tap table (built on the host, srcnn_ctx.cu): x = left + (index of tap A), y = wA bits, z = wB bits,
+ * w = left + (index of tap B); B is the tap whose weight is 0 or a power of two */
 template <int D, bool CONV>
 __global__ void __launch_bounds__(256)
 color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc, size_t cstride, unsigned w, unsigned src_row0,
@@ -168,12 +168,16 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
                     unsigned ow, unsigned row0, unsigned nrows, unsigned rpc, uint8_t* __restrict__ out, uint8_t* __restrict__ conv)
 {
     constexpr int NC = D - 1;
-    __shared__ float tS[2][NC][kUpMaxCols];       /* the intermediate (vertically resampled) plane, this CTA's columns; by row parity */
-    const unsigned xb = blockIdx.x * kUpBlockPx;
-    const unsigned xe = min(xb + kUpBlockPx, ow) - 1;                 /* last pixel of this CTA */
-    const int4 hb = __ldg(hpack + xb), he = __ldg(hpack + xe);
+    /* the intermediate (vertically resampled) plane: every WARP stages the source columns of its own 128 pixels (so rows
+     * need only __syncwarp, warps run independently), double-buffered by row parity */
+    __shared__ float tS[8][2][NC][kUpMaxCols];
+    const unsigned wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned xw = blockIdx.x * kUpBlockPx + wq * kUpWarpPx;     /* first pixel of this warp */
+    if (xw >= ow) return;                                             /* (whole warps only: no block barrier below) */
+    const unsigned xe = min(xw + kUpWarpPx, ow) - 1;                  /* last pixel of this warp */
+    const int4 hb = __ldg(hpack + xw), he = __ldg(hpack + xe);
     const int c_lo = min(hb.x, hb.w), ncols = max(he.x, he.w) - c_lo + 1;   /* source columns [c_lo, c_lo + ncols) */
-    const unsigned x0 = xb + threadIdx.x * 4;
+    const unsigned x0 = xw + lane * 4;
     const bool active = x0 < ow;
     int ia[4], ib[4]; float hA[4], hB[4];
     #pragma unroll
@@ -183,7 +187,7 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
     }
     const unsigned ry0 = blockIdx.y * rpc, ry1 = min(ry0 + rpc, nrows);
     /* software pipeline over the rows: the source samples (and Y') of row r+1 are requested before row r is computed, so
-     * their latency hides behind the colour arithmetic -- one barrier per row, the staging buffer alternates by row parity */
+     * their latency hides behind the colour arithmetic */
     float pa[kUpIters][NC], pb[kUpIters][NC], pvA = 0.f, pvB = 0.f;
     float4 py = make_float4(0.f, 0.f, 0.f, 0.f);
     auto prefetch = [&](unsigned ry) {
@@ -193,7 +197,7 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
         const float* rB = csrc + (size_t)(vp.w - (int)src_row0) * w + c_lo;
         #pragma unroll
         for (int it = 0; it < kUpIters; it++) {
-            const int j = threadIdx.x + 256 * it;
+            const int j = (int)lane + 32 * it;
             if (j < ncols) {
                 #pragma unroll
                 for (int k = 0; k < NC; k++) { pa[it][k] = __ldg(rA + k * cstride + j); pb[it][k] = __ldg(rB + k * cstride + j); }
@@ -203,19 +207,19 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
     };
     if (ry0 < ry1) prefetch(ry0);
     for (unsigned ry = ry0; ry < ry1; ry++) {
-        float (*t)[kUpMaxCols] = tS[ry & 1];
+        float (*t)[kUpMaxCols] = tS[wq][ry & 1];
         #pragma unroll
         for (int it = 0; it < kUpIters; it++) {
-            const int j = threadIdx.x + 256 * it;
+            const int j = (int)lane + 32 * it;
             if (j < ncols) {
                 #pragma unroll
                 for (int k = 0; k < NC; k++) t[k][j] = mix2f(pvA, pa[it][k], pvB, pb[it][k]);
             }
         }
         const float4 y4 = py;
-        __syncthreads();                /* (the other parity's buffer was last read before the previous row's barrier) */
+        __syncwarp();                   /* (the other parity's buffer was last read before the previous row's __syncwarp) */
         if (ry + 1 < ry1) prefetch(ry + 1);
-        if (!active) continue;
+        if (!active) continue;              /* (a lane without pixels still staged its columns above) */
         const size_t i0 = (size_t)ry * ow + x0;
         const float Y[4] = { y4.x, y4.y, y4.z, y4.w };
         uint32_t bytes[4 * D];
@@ -244,12 +248,12 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
     }
 }
 
-/* host-side: the source columns one CTA (kUpBlockPx output pixels) reads fit its shared-memory row, and lefts are monotonic */
+/* host-side: the source columns one warp (kUpWarpPx output pixels) reads fit its shared-memory row, and lefts are monotonic */
 bool color_out_up_quads_ok(const int* h_hcl, unsigned ow)
 {
     if (ow % 4) return false;
-    for (unsigned x = 0; x < ow; x += kUpBlockPx) {
-        const unsigned e = (x + kUpBlockPx < ow ? x + kUpBlockPx : ow) - 1;
+    for (unsigned x = 0; x < ow; x += kUpWarpPx) {
+        const unsigned e = (x + kUpWarpPx < ow ? x + kUpWarpPx : ow) - 1;
         if (h_hcl[e] + 1 - h_hcl[x] + 1 > kUpMaxCols) return false;
     }
     for (unsigned x = 1; x < ow; x++) if (h_hcl[x] < h_hcl[x - 1]) return false;
@@ -264,8 +268,16 @@ bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, uns
     if (!vc.pack2 || !hc.pack2 || (ow % 4) || row1 <= row0) return false;
     if (!al(yp, 16) || !al(out, d == 4 ? 16 : 4) || (conv && !al(conv, 4))) return false;
     const unsigned gx = (ow + kUpBlockPx - 1) / kUpBlockPx, nrows = row1 - row0;
-    unsigned rpc = (unsigned)(((size_t)gx * nrows) / (148u * 8u));          /* aim at >= 8 CTAs per SM */
-    rpc = rpc < 2 ? 2 : (rpc > (unsigned)kUpRowsMax ? (unsigned)kUpRowsMax : rpc);
+    /* rows per CTA: 4 CTAs of 64-72 registers x 256 threads are resident per SM; pick the row count that minimises
+     * (number of waves) x (rows + one row-time of prologue), i.e. avoids a nearly empty last wave */
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148; }
+    unsigned rpc = 2; size_t best = ~(size_t)0;
+    for (unsigned r = 2; r <= (unsigned)kUpRowsMax; r++) {
+        const size_t ctas = (size_t)gx * ((nrows + r - 1) / r), waves = (ctas + (size_t)sms * 4 - 1) / ((size_t)sms * 4);
+        const size_t cost = waves * (r + 1);
+        if (cost <= best) { best = cost; rpc = r; }
+    }
     dim3 grid(gx, (nrows + rpc - 1) / rpc);
     if (grid.y > 65535u) return false;
 #define SRCNN_COU(D_, C_) color_out_up_kernel<D_, C_><<<grid, 256, 0, s>>>(yp, csrc, cstride, w, src_row0, \
