@@ -35,7 +35,7 @@ ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-NCU_CONV_DRAM_BYTES = 17225984   # conv_tc_kernel at C2: 17.175 MB read + 0.051 MB written (profiles/r1_ncu_summary.md)
+NCU_CONV_DRAM_BYTES = 17243904   # conv_tc_kernel at C2: 17.172 MB read + 0.072 MB written (profiles/r1_ncu_summary.md)
 FLOP_PER_PX = 16064            # conv I 81*64 + conv II 64*32 + conv III 25*32 MACs, x2
 WORKLOADS = {
     # name: (h, w, d, multiply, filter, description)
