@@ -10,10 +10,11 @@ namespace srcnn {
 
 __device__ __forceinline__ uint32_t to_u8(float f)
 {
-    /* (unsigned char)MAX(0.f, MIN(255.f, f)) with MIN(a,b) = a<b?a:b, truncating cast */
-    f = (255.f < f) ? 255.f : f;
-    f = (0.f > f) ? 0.f : f;
-    return __float2uint_rz(f);
+    /* (unsigned char)MAX(0.f, MIN(255.f, f)) with MIN(a,b) = a<b?a:b, truncating cast.  A float -> u8 conversion in PTX
+     * clamps to the destination range, so one cvt.rzi.u8.f32 is that whole expression (no NaNs arise on this path). */
+    uint32_t u;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(u) : "f"(f));
+    return u;
 }
 
 __device__ __forceinline__ void rgb_of(float y, float cb, float cr, uint32_t& r, uint32_t& g, uint32_t& b)
