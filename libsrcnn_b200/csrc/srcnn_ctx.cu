@@ -145,7 +145,8 @@ struct srcnn_b200_ctx {
     unsigned long long launches = 0;
     std::string err;
     /* host pipeline (srcnn_b200_pass_host_rows) */
-    size_t strip_bytes = (size_t)8 << 20;     /* result bytes per pipelined sub-strip (SRCNN_B200_STRIP_MB)          */
+    size_t strip_bytes = 0;                   /* result bytes per pipelined sub-strip; 0 = by destination: 4 MB into pinned
+                                                 memory, 8 MB into pageable memory (measured, tools/e2e_probe.py); SRCNN_B200_STRIP_MB */
     bool stage_pageable = true;               /* pageable results go through pinned staging (SRCNN_B200_STAGE=0: off) */
     std::vector<cudaEvent_t> pipe_ev;         /* 3 per sub-strip: uploaded, computed, downloaded                      */
     HostCopier copier;
@@ -646,7 +647,8 @@ int srcnn_b200_pass_host_rows(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned 
      * while in flight. */
     const size_t row_bytes = (size_t)p.ow * d;
     const size_t out_bytes = (size_t)(row1 - row0) * row_bytes, conv_bytes = (size_t)(row1 - row0) * p.ow;
-    unsigned nstrips = (unsigned)std::min<size_t>((out_bytes + ctx->strip_bytes / 2) / ctx->strip_bytes, kMaxPipeStrips);
+    const size_t strip_bytes = ctx->strip_bytes ? ctx->strip_bytes : (size_t)(host_is_pinned(out_rows) ? 4 : 8) << 20;
+    unsigned nstrips = (unsigned)std::min<size_t>((out_bytes + strip_bytes / 2) / strip_bytes, kMaxPipeStrips);
     nstrips = std::max(1u, std::min(nstrips, (row1 - row0) / 64u));
     Plan sp[kMaxPipeStrips];
     for (unsigned i = 0; i < nstrips; i++) {
