@@ -98,7 +98,7 @@ class ClockSampler:
                 "reasons": [n for n, b in names if bits & b], "samples": len(rows), "source": "NVML, 2 ms period, timed region only"}
 
 
-def cpu_reference_run(h, w, d, m, filt, conv_on, budget_s=12.0):
+def cpu_reference_run(h, w, d, m, filt, conv_on, budget_s=12.0, check_ctx=None):
     """the reference's CPU implementation (oracle/_ref; the plain-C port if the reference was not compiled) on a
     bounded sample: a horizontal crop of the workload frame sized for a few seconds of CPU work"""
     import oracle_lib as O
@@ -111,10 +111,18 @@ def cpu_reference_run(h, w, d, m, filt, conv_on, budget_s=12.0):
     runs, best = 1, dt
     while runs < 3 and (time.perf_counter() - t0) + best < budget_s:
         t1 = time.perf_counter(); orc.process(img, m, filt, False, conv_on); best = min(best, time.perf_counter() - t1); runs += 1
-    return dict(value=ow * oh / best / 1e6, unit="output MP/s", cores=orc.threads,
-                kind="reference" if orc.kind == "reference" else "port",
-                sample="%dx%dx%d crop of the workload frame -> %dx%d, best of %d run(s), %.2f s each, OpenMP threads=%d"
-                       % (w, sh, d, ow, oh, runs, best, orc.threads)), best, ow * oh
+    res = dict(value=ow * oh / best / 1e6, unit="output MP/s", cores=orc.threads,
+               kind="reference" if orc.kind == "reference" else "port",
+               sample="%dx%dx%d crop of the workload frame -> %dx%d, best of %d run(s), %.2f s each, OpenMP threads=%d"
+                      % (w, sh, d, ow, oh, runs, best, orc.threads))
+    if check_ctx is not None:
+        # the parity gate of SURVEY 8(d), on the same sample: the GPU result of the crop against the CPU result just computed
+        got, _ = check_ctx.pass_host(img, m, filt, conv_on)
+        diff = np.abs(got.reshape(-1).astype(np.int16) - out.astype(np.int16))
+        res["parity"] = {"max_abs_lsb": int(diff.max()), "psnr_db": round(float(O.psnr(got.reshape(-1), out)), 2),
+                         "gate": "<= 1 LSB and >= 50 dB against the CPU result of the same sample",
+                         "ok": bool(diff.max() <= 1 and O.psnr(got.reshape(-1), out) >= 50.0)}
+    return res, best, ow * oh
 
 
 def run_reference(args, wl):
@@ -283,7 +291,7 @@ def main():
     stage_avg = {k: float(np.mean([s[k] for s in stage_ms])) for k in stage_ms[0]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu, _, _ = cpu_reference_run(h, w, d, m, filt, conv_on)
+        cpu, _, _ = cpu_reference_run(h, w, d, m, filt, conv_on, check_ctx=ctx)
     line = {
         "metric": "output MP/s, SRCNN x2 to 4K (ProcessSRCNN hot path)", "value": value, "unit": "output MP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
