@@ -143,7 +143,7 @@ def run_reference(args, wl):
     tot = sum(dt for _, dt in vals)
     v = px * len(vals) / tot / 1e6
     cb["value"] = v
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "output MP/s, SRCNN x2 to 4K (ProcessSRCNN hot path)", "value": v, "unit": "output MP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(vals) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -151,7 +151,23 @@ def run_reference(args, wl):
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "output MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+def emit(line):
+    """the ONE JSON line goes to the process's original stdout; everything else that libraries write to fd 1 (NCCL prints
+    its version banner there) has been diverted to stderr by quiet_stdout()"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
@@ -167,6 +183,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args, wl)
 
@@ -319,7 +336,7 @@ def main():
         "stage_ms": stage_avg,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
