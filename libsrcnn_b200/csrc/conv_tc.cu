@@ -5,27 +5,30 @@
  *
  * Mapping.  A persistent CTA (one per SM) owns bands of 128 adjacent image columns (124 output columns + 2x2 halo for
  * conv III) and walks down row segments; TMEM lane t = image column c0 + t.  For every image row the three layers are
- * three chained M=128 implicit GEMMs whose A operand lives in TENSOR MEMORY (written by tcgen05.st: lane = pixel,
+ * chained M=128 implicit GEMMs whose A operand lives in TENSOR MEMORY (written by tcgen05.st: lane = pixel,
  * column = two packed FP16 K elements) and whose B operand (the weights) sits in shared memory in the canonical
  * K-major no-swizzle core-matrix layout:
  *
- *   conv I  : A1[px][k = 10*i + j] = Y16(q-4+i, c-4+j)   K = 96 (81 taps; the j = 9 column and k >= 92 carry zero
- *             weights; k = 90/91 are constant 1.0 inputs whose weights are the bias split hi/lo)          N = 64
- *             each thread keeps its 9x10 window in registers and rolls it down one row per step, so building the
- *             im2col operand costs six 32-bit shared loads per pixel instead of 81
- *   conv II : A2[px][k] = fp16(ReLU(D1[px][k]))          K = 64, N = 32   (bias + ReLU in the FP32 epilogue)
- *   conv III: "taps as N": Z[px][tap] = sum_ch A3[px][ch] * W3[ch][tap]   K = 32, N = 32 (25 used); the 5x5 spatial
- *             gather out(r,c) = sum_{dy,dx} Z[(r+dy, c+dx)][tap(dy,dx)] is then 25 FP32 adds per pixel: the dy part
- *             accumulates in registers while the rows stream by, the dx part crosses lanes through shared memory.
+ *   conv I  : A1[px][k = 10*slot + j] = Y16(row held in ring slot `slot`, c-4+j)   K = 96 (81 taps; the j = 9 column and
+ *             k >= 92 carry zero weights; k = 90/91 are constant 1.0 inputs whose weights are the bias split hi/lo), N = 64.
+ *             The 9-row window is a ring of 9 register slots per thread; the issuer picks one of 9 ROTATED weight images
+ *             (row mod 9) instead of rolling the window, so a new row costs six 32-bit shared loads and only the two
+ *             slots that changed since the same-parity row two rows earlier (10 TMEM columns) are rewritten.
+ *   conv II : A2[px][k] = fp16(ReLU(D1[px][k]))          K = 64, N = 32, plus one K = 16 step for the bias whose A operand
+ *             is the last K-step of A1 (it contains the constant-1 inputs; all other k meet zero weights).
+ *   conv III: on the tensor core too, one SET per pair of output rows: K = 6 conv II rows x 32 channels out of an 8-row
+ *             ring in TMEM, N = 16 (2 rows x 5 dx); the remaining 5-term dx sum crosses lanes through shared memory in
+ *             the gather group, then bias, clamp, FP32 store.
  *
- * Warp specialisation (20 warps): TMA producer (Y16 row chunks -> 4-stage smem ring), MMA issuer (one thread),
- * TMEM allocator, and four 4-warp groups -- im2col, epilogue I, epilogue II, gather/store -- chained by mbarriers
- * with every TMEM operand / accumulator region double-buffered, so the tensor pipe works on row n while the groups
- * prepare row n+1 and drain rows n-1, n-2.
+ * Warp specialisation (24 warps): TMA producer (Y16 row chunks -> 4-stage smem ring), three single-lane MMA issuers
+ * (one per layer), and five 4-warp groups -- im2col, epilogue I x2 (one per row parity), epilogue II, gather/store --
+ * chained by mbarriers with every TMEM operand / accumulator region double-buffered (A3: 4-pair ring), so the tensor pipe
+ * works on row n while the groups prepare row n+1 and drain rows n-1, n-2.  The issuing lanes are the critical threads
+ * of the pipeline: their instruction streams are kept as short as possible.
  *
  * Border semantics follow the reference exactly: conv I clamps Y coordinates (the Y16 plane is replicate-padded by
- * the pack kernel), conv III clamps the coordinates of the conv II plane itself (src/libsrcnn.cpp:461-491), which
- * here becomes a clamp on the row / lane index of Z in the gather.
+ * the front end), conv III clamps the coordinates of the conv II plane itself (src/libsrcnn.cpp:461-491), which
+ * here becomes a choice of ring slot per K-step (rows) and a clamp on the lane index in the gather (columns).
  *
  * Arithmetic: FP16 operands (round-to-nearest), FP32 accumulation in TMEM, FP32 epilogues.  SURVEY.md 7.4 shows this
  * keeps |dY'| < 1 (final 8-bit output within 1 LSB); tests/test_parity_gpu.py asserts it against the oracle.
