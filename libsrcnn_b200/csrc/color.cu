@@ -2,6 +2,7 @@
  *
  *  color_in  = reference converImgU8toYCbCr   (src/libsrcnn.cpp:233-272)
  *  color_out = reference convertImgF32XtoImgU8 (src/libsrcnn.cpp:274-308) + conv-output plane (:889-915)
+ *  color_out_up = the same with the x2 chroma / alpha resampling (FRAWResizeEngine::scale, bilinear / box) folded in
  *
  * Every FP32 operation uses the round-to-nearest non-fused intrinsics in the reference's association order
  * (its x86-64 -O2 build has no FMA contraction), so both kernels are bit-exact against the oracle.

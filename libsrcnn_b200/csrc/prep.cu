@@ -1,6 +1,7 @@
 /* Fused front end of one pass: colour-in + both resampling passes + the conv-input pack, one kernel, one trip to HBM.
  *
- *   u8 RGB(A) source rows  ->  Cb, Cr, (A) FP32 planes at output size  +  replicate-padded FP16 Y plane (conv input)
+ *   u8 RGB(A) source rows  ->  replicate-padded FP16 Y plane (conv input)  +  Cb, Cr, (A) as FP32 planes: at SOURCE size
+ *                              on the x2 route (colour-out resamples them, color.cu), at output size otherwise
  *                              (+ the FP32 Y plane when asked for: bit-exact conv mode / plane getters)
  *
  * = reference converImgU8toYCbCr (src/libsrcnn.cpp:233-272) followed by FRAWResizeEngine::scale in its UPSCALE order,
@@ -10,8 +11,8 @@
  * A CTA owns a TH x TW tile of the output.  The source footprint of the tile (from the compact contribution tables) is
  * colour-converted once into shared memory, the vertical pass runs shared -> shared, the horizontal pass shared ->
  * registers -> global.  The 4-byte planes of the unfused sequence (source planes, intermediate plane, FP32 Y) never
- * reach HBM: at 1920x1080 -> 3840x2160 RGB the front end moves 6 + 66 + 17 MB instead of 6 + 25 + 25 + 50 + 50 + 100
- * + 33 + 17 MB.
+ * reach HBM: at 1920x1080 -> 3840x2160 RGB the front end moves 6 + 17 + 17 MB (x2 route; 6 + 66 + 17 MB with output-size
+ * chroma planes) instead of 6 + 25 + 25 + 50 + 50 + 100 + 33 + 17 MB.
  *
  * Arithmetic is that of the separate kernels (resize.cu, color.cu) and therefore bit-exact against the oracle:
  * unfused FP32 colour conversion in the reference's association order; per destination sample a double accumulator
