@@ -225,6 +225,9 @@ def main():
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
 
     def step():
+        if nfr > 1:          # a batch of frames: srcnn_b200_batch_device (small frames share one fused-conv launch per group)
+            ctx.batch_device(d_src.data_ptr(), nfr, w, h, d, m, filt, d_out.data_ptr(), d_conv.data_ptr() if conv_on else 0)
+            return
         for i in range(nfr):
             ctx.pass_device(d_src[i].data_ptr(), w, h, d, m, filt, d_out[i].data_ptr(),
                             d_conv[i].data_ptr() if conv_on else 0, rows=(r0, r1))
@@ -254,7 +257,8 @@ def main():
         step()
         ev[i][1].record(stream)
         ctx.sync()                                                         # also collects the per-kernel events
-        t = ctx.timings(); conv_ms.append(t["conv"]); stage_ms.append(t)   # (of the step's last frame)
+        t = ctx.timings(); conv_ms.append(t["conv"]); stage_ms.append(t)   # (of the step's last frame / frame group)
+        conv_frames = ctx.last_group
     barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
@@ -311,6 +315,7 @@ def main():
         h2d_bytes = int(imgs.nbytes)
     conv_avg_ms = float(np.mean(conv_ms))
     conv_px = (r1 - r0) * ow                                       # one launch = one frame (or strip) of this rank
+    conv_px *= conv_frames                                         # batches: the step's last conv launch covered a group of frames
     achieved_tf = conv_px * FLOP_PER_PX / (conv_avg_ms * 1e-3) / 1e12
     stage_avg = {k: float(np.mean([s[k] for s in stage_ms])) for k in stage_ms[0]}
     cpu = None

@@ -94,6 +94,12 @@ int srcnn_b200_process_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w,
 int srcnn_b200_batch_host(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n, unsigned w, unsigned h,
                           unsigned d, float multiply, int filter, uint8_t* out, uint8_t* conv);
 
+/* The same batch with DEVICE pointers (frames, out, conv on the context's device), enqueued on the context's stream like
+ * srcnn_b200_pass_device.  Small frames are processed in groups whose fused convolution is ONE kernel launch over all
+ * frames of the group (a persistent kernel is not filled by a single small frame); large frames run one by one. */
+int srcnn_b200_batch_device(srcnn_b200_ctx* ctx, const void* d_frames, unsigned n, unsigned w, unsigned h,
+                            unsigned d, float multiply, int filter, void* d_out, void* d_conv);
+
 /* pinned host memory for fast DMA (cudaHostAlloc / cudaFreeHost) */
 void* srcnn_b200_host_alloc(size_t bytes);
 void  srcnn_b200_host_free(void* p);
@@ -113,6 +119,8 @@ int srcnn_b200_set_timing(srcnn_b200_ctx* ctx, int on);
 int srcnn_b200_last_timings(srcnn_b200_ctx* ctx, float* ms7);
 /* kernels launched by this context since creation */
 unsigned long long srcnn_b200_launch_count(const srcnn_b200_ctx* ctx);
+/* frames covered by the last pass (1) or frame group of a batch -- what srcnn_b200_last_timings then describes */
+unsigned srcnn_b200_last_group(const srcnn_b200_ctx* ctx);
 
 /* ---- single stages on host data (per-stage parity against the oracle) ---------------------------------------- */
 /* reference converImgU8toYCbCr, src/libsrcnn.cpp:233-272; planes = d pointers to w*h floats */

@@ -58,6 +58,7 @@ def lib():
         L.srcnn_b200_stream.argtypes = [vp]; L.srcnn_b200_stream.restype = vp
         L.srcnn_b200_process_host.argtypes = [vp, vp, u, u, u, f, i, i, vp, vp]
         L.srcnn_b200_batch_host.argtypes = [vp, vp, u, u, u, u, f, i, vp, vp]
+        L.srcnn_b200_batch_device.argtypes = [vp, vp, u, u, u, u, f, i, vp, vp]
         L.srcnn_b200_host_alloc.argtypes = [C.c_size_t]; L.srcnn_b200_host_alloc.restype = vp
         L.srcnn_b200_host_free.argtypes = [vp]; L.srcnn_b200_host_free.restype = None
         L.srcnn_b200_get_plane.argtypes = [vp, i, vp, C.c_size_t, C.POINTER(u), C.POINTER(u), C.POINTER(u)]
@@ -65,6 +66,7 @@ def lib():
         L.srcnn_b200_set_keep_planes.argtypes = [vp, i]
         L.srcnn_b200_last_timings.argtypes = [vp, _f32p]
         L.srcnn_b200_launch_count.argtypes = [vp]; L.srcnn_b200_launch_count.restype = C.c_ulonglong
+        L.srcnn_b200_last_group.argtypes = [vp]; L.srcnn_b200_last_group.restype = C.c_uint
         L.srcnn_b200_stage_color_in.argtypes = [vp, vp, u, u, u, C.POINTER(vp)]
         L.srcnn_b200_stage_resize.argtypes = [vp, vp, u, u, u, u, i, vp]
         L.srcnn_b200_stage_conv.argtypes = [vp, vp, u, u, i, vp]
@@ -250,6 +252,11 @@ class Context:
                  "batch_host")
         return out, conv
 
+    def batch_device(self, d_frames, n, w, h, d, multiply, filt, d_out, d_conv=0):
+        """device pointers (ints) of n contiguous frames / results; asynchronous on the context's stream"""
+        self._ck(self.L.srcnn_b200_batch_device(self.h, d_frames, n, w, h, d, multiply, int(filt), d_out, d_conv or None),
+                 "batch_device")
+
     # ---- introspection ----------------------------------------------------------------------------------
     def get_plane(self, which, shape_hint):
         oh, ow = shape_hint
@@ -273,6 +280,10 @@ class Context:
     @property
     def launches(self):
         return int(self.L.srcnn_b200_launch_count(self.h))
+
+    @property
+    def last_group(self):
+        return int(self.L.srcnn_b200_last_group(self.h))
 
     # ---- single stages ----------------------------------------------------------------------------------
     def color_in(self, img):

@@ -267,6 +267,9 @@ struct TcParams {
     int d;
     int row0, row1;
     int bands, ppb;             /* column bands; row pairs per band = ceil((row1-row0) / 2) */
+    int nframes;                /* same-geometry frames in this launch: frame f's conv-input plane starts at plane row
+                                   f * y16_rows, its Y' at out + f * out_fstride */
+    size_t out_fstride;
     const unsigned char* wimg;  /* B1 x 9 rotations | B2 | B2-bias | B3 operand images */
 #ifdef SRCNN_PROF
     long long* prof;
@@ -278,11 +281,11 @@ struct TcParams {
  * the rows [ra, rb); it streams the conv II rows q = ra-2 .. ra-3+nrows, nrows even (output rows are produced in
  * pairs; an odd tail computes one discarded extra row).  Long contiguous units keep the per-unit cost (4 halo rows,
  * 8 window-fill rows, pipeline fill and drain) to about two per CTA. */
-struct Unit { int band, ra, rb, npairs, nrows; };
+struct Unit { int frame, band, ra, rb, npairs, nrows; };
 struct Span { int s, e, nunits; };
 __device__ __forceinline__ Span span_of(const TcParams& p)
 {
-    const long long T = (long long)p.bands * p.ppb;
+    const long long T = (long long)p.nframes * p.bands * p.ppb;      /* (frame, band) pairs are walked like bands of one image */
     Span x;
     x.s = (int)(T * blockIdx.x / gridDim.x);
     x.e = (int)(T * (blockIdx.x + 1) / gridDim.x);
@@ -292,9 +295,11 @@ __device__ __forceinline__ Span span_of(const TcParams& p)
 __device__ __forceinline__ Unit unit_of(const TcParams& p, const Span& sp, int k)
 {
     Unit x;
-    x.band = sp.s / p.ppb + k;
-    const int p0 = k == 0 ? sp.s - x.band * p.ppb : 0;
-    const int p1 = min(p.ppb, sp.e - x.band * p.ppb);
+    const int gb = sp.s / p.ppb + k;                  /* band index over all frames */
+    x.frame = gb / p.bands;
+    x.band = gb - x.frame * p.bands;
+    const int p0 = k == 0 ? sp.s - gb * p.ppb : 0;
+    const int p1 = min(p.ppb, sp.e - gb * p.ppb);
     x.ra = p.row0 + 2 * p0;
     x.rb = min(p.row0 + 2 * p1, p.row1);
     x.npairs = p1 - p0;
@@ -363,7 +368,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             for (int u = 0; u < span.nunits; u++) {
                 const Unit un = unit_of(p, span, u);
                 const int x0 = (un.band * kBandCols + 2) & ~7;            /* 16 B aligned box origin */
-                const int yr0 = un.ra - p.row0;                           /* plane row of image row ra-6 */
+                const int yr0 = un.frame * p.y16_rows + un.ra - p.row0;   /* plane row of image row ra-6 (of this frame) */
                 const int nch = (un.nrows + 8 + CH_ROWS - 1) / CH_ROWS;
                 for (int j = 0; j < nch; j++, ck++) {
                     const uint32_t s = ck % NST, k = ck / NST;
@@ -681,7 +686,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 }
             };
             load_chroma(un.ra);
-            float* odst = (!FUSE || p.out) ? p.out + ((size_t)(un.ra - p.row0) * p.dw + c) : nullptr;   /* two rows further per set */
+            float* odst = (!FUSE || p.out) ? p.out + ((size_t)un.frame * p.out_fstride + (size_t)(un.ra - p.row0) * p.dw + c) : nullptr;   /* two rows further per set */
             const size_t ostep = 2 * (size_t)p.dw;
             #pragma unroll 1
             for (int pp = 0; pp < un.npairs; pp++, sg++, odst += ostep) {
@@ -845,9 +850,12 @@ void conv_tc_destroy(ConvTcState* st)
 const char* conv_tc_error(const ConvTcState* st) { return st ? st->err.c_str() : "no state"; }
 
 int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, unsigned dh,
-                   float* out, unsigned row0, unsigned row1, int num_sms, cudaStream_t s, const ConvTcColor* col)
+                   float* out, unsigned row0, unsigned row1, int num_sms, cudaStream_t s, const ConvTcColor* col,
+                   unsigned nframes, size_t out_fstride)
 {
     TcParams p;
+    if (nframes == 0 || (nframes > 1 && col)) { st->err = "frame groups: no fused colour-out"; return 1; }
+    p.nframes = (int)nframes; p.out_fstride = out_fstride;
     p.cb = col ? col->cb : nullptr; p.cr = col ? col->cr : nullptr; p.al = col ? col->al : nullptr;
     p.rgb = col ? col->rgb : nullptr; p.conv8 = col ? col->conv8 : nullptr; p.d = col ? (int)col->d : 3;
     /* the RGBA store is one 32-bit word per pixel */
@@ -861,7 +869,7 @@ int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, u
     p.wimg = st->d_wimg;
 
     CUtensorMap map;
-    const cuuint64_t gdim[2] = { (cuuint64_t)g.pitch, (cuuint64_t)g.rows };
+    const cuuint64_t gdim[2] = { (cuuint64_t)g.pitch, (cuuint64_t)g.rows * nframes };
     const cuuint64_t gstr[1] = { (cuuint64_t)g.pitch * 2 };
     const cuuint32_t box[2] = { BOX_W, CH_ROWS };
     const cuuint32_t estr[2] = { 1, 1 };
@@ -871,7 +879,7 @@ int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, u
     if (cr != CUDA_SUCCESS) { st->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"; return 1; }
 
     /* one persistent CTA per SM; tiny inputs: at least ~16 row pairs per CTA so that the per-unit costs stay amortised */
-    const long long T = (long long)p.bands * p.ppb, want = (T + 15) / 16;
+    const long long T = (long long)p.nframes * p.bands * p.ppb, want = (T + 15) / 16;
     const int grid = (int)(want < 1 ? 1 : (want < num_sms ? want : num_sms));
 #ifdef SRCNN_PROF
     static long long* d_prof = nullptr;

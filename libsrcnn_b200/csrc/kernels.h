@@ -97,9 +97,12 @@ struct ConvTcColor {
     unsigned d = 3;
 };
 /* out (FP32 Y', rows [row0,row1) x dw) may be NULL when col.rgb is given */
+/* nframes > 1: a group of same-geometry frames in ONE launch (the persistent CTAs then amortise pipeline fill / drain over
+ * all of them -- what small frames need): frame f's conv-input plane follows frame f-1's (g.rows rows each), its Y' lies at
+ * out + f * out_fstride */
 int  launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, unsigned dh,
                     float* out, unsigned row0, unsigned row1, int num_sms, cudaStream_t s,
-                    const ConvTcColor* col = nullptr);
+                    const ConvTcColor* col = nullptr, unsigned nframes = 1, size_t out_fstride = 0);
 const char* conv_tc_error(const ConvTcState* st);
 
 /* colour-out: Y' + Cb/Cr/(A) -> interleaved u8 (+ optional u8 conv plane); all arrays are `npix` long views */

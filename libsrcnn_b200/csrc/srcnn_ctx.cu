@@ -154,7 +154,9 @@ struct srcnn_b200_ctx {
     bool keep_planes = false;                 /* also write the FP32 interpolated Y plane in tensor mode (getters)    */
     bool last_has_y32 = false;
     bool last_has_chroma = true;              /* output-size Cb / Cr / A planes of the last pass exist (getters 1-3)   */
+    bool group_frames = true;                 /* batches: one conv launch per group of small frames (SRCNN_B200_GROUP=0) */
     bool chroma_up = true;                    /* x2: chroma resampled inside colour-out (SRCNN_B200_CHROMA_UP=0: off)  */
+    unsigned last_group = 1;                  /* frames covered by the last pass / group (and by its timings)          */
     bool last_has_yp = true;                  /* the FP32 network output Y' of the last pass exists (plane getter 4)  */
     bool fuse_color = false;                  /* tensor mode: colour-out inside the conv kernel's store stage (SRCNN_B200_FUSE_COLOR=1).
                                                * Off by default: measured 0.202 ms fused vs 0.155 + 0.023 ms separate per 4K frame --
@@ -434,7 +436,7 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
     }
     st.mark();
     CK(cudaGetLastError());
-    ctx->last = p; ctx->have_last = true; ctx->last_plane_stride = ps_dst;
+    ctx->last = p; ctx->have_last = true; ctx->last_plane_stride = ps_dst; ctx->last_group = 1;
     return 0;
 }
 
@@ -450,6 +452,78 @@ int collect_timing(srcnn_b200_ctx* ctx)
     float v = 0.f;
     if (cudaEventElapsedTime(&v, ctx->ev[0], ctx->ev[6]) != cudaSuccess) v = -1.f;
     ctx->ms[6] = v;
+    return 0;
+}
+
+
+/* ---- frame groups (same geometry): G front-end launches, ONE fused-conv launch over all G frames, G colour-out
+ * launches.  Small frames do not fill the persistent conv kernel (a 1024 x 1024 result is ~31 row pairs per CTA, a third of
+ * them pipeline fill and halo); a group amortises that.  Only the product route is grouped: tensor-core conv, fused
+ * front end, chroma resampled inside colour-out; anything else runs frame by frame through run_pass. */
+unsigned group_size(const srcnn_b200_ctx* ctx, const Plan& p, unsigned n)
+{
+    if (ctx->conv_mode != SRCNN_B200_CONV_TENSOR || !ctx->fuse_front || !ctx->chroma_up || ctx->keep_planes ||
+        ctx->fuse_color || !ctx->group_frames) return 1;
+    if (p.hfirst || !p.need_h || !p.need_v || (p.ow % 4) || p.r0 != 0 || p.r1 != p.oh) return 1;
+    const size_t px = (size_t)p.ow * p.oh;
+    const size_t g = ((size_t)8 << 20) / (px ? px : 1);                  /* groups of up to ~8 Mpx of output */
+    return (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(g, 16), n));
+}
+
+/* d_src: G frames of w*h*d bytes; d_out: G frames of ow*oh*d; d_conv: G frames of ow*oh or NULL.  Returns 1 if the geometry
+ * is not covered by the grouped route (nothing launched; the caller falls back to run_pass per frame). */
+int run_group(srcnn_b200_ctx* ctx, Plan& p, unsigned G, const uint8_t* d_src, uint8_t* d_out, uint8_t* d_conv)
+{
+    TableDev *vy = nullptr, *vc = nullptr, *hy = nullptr, *hc = nullptr;
+    int rc;
+    if ((rc = get_table(ctx, p.fy, p.oh, p.h, &vy))) return rc;
+    if ((rc = get_table(ctx, p.fc, p.oh, p.h, &vc))) return rc;
+    if ((rc = get_table(ctx, p.fy, p.ow, p.w, &hy))) return rc;
+    if ((rc = get_table(ctx, p.fc, p.ow, p.w, &hc))) return rc;
+    source_rows(vy->host, vc->host, p.e0, p.e1, p.s0, p.s1);
+    const size_t ib = (size_t)p.w * p.h * p.d, ob = (size_t)p.ow * p.oh * p.d, cb = (size_t)p.ow * p.oh;
+    if (!prep_supported(vy->view, vc->view, hy->view, hc->view) || !prep_chroma_handover(vc->view, hc->view) || !hc->quads_ok ||
+        ((uintptr_t)d_out % 16) || (ob % 16) || (d_conv && (((uintptr_t)d_conv % 4) || (cb % 4)))) return 1;
+    auto al = [](size_t n) { return (n + 63) / 64 * 64; };
+    const unsigned srows = p.s1 - p.s0;
+    const size_t ps_csrc = al((size_t)srows * p.w), csrc_f = ps_csrc * (p.d - 1);
+    const Y16Geom g = y16_geometry(p.ow, p.oh);
+    const size_t y16_f = (size_t)g.pitch * g.rows, yp_f = al((size_t)p.ow * p.oh);
+    CK(ctx->y16.ensure(y16_f * G * sizeof(__half)));
+    CK(ctx->chroma_src.ensure(csrc_f * G * sizeof(float)));
+    CK(ctx->yprime.ensure(yp_f * G * sizeof(float)));
+    __half* Y16 = static_cast<__half*>(ctx->y16.p);
+    float* CS = static_cast<float*>(ctx->chroma_src.p);
+    float* Yp = static_cast<float*>(ctx->yprime.p);
+    cudaStream_t s = ctx->stream;
+    Stamp st(ctx);                                                  /* timings then describe the whole group */
+    for (unsigned f = 0; f < G; f++) {
+        if (!launch_prep(d_src + f * ib + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, 0, false,
+                         Y16 + f * y16_f, g, p.r0, vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(),
+                         vc->host.cleft.data(), hy->host.cleft.data(), hc->host.cleft.data(), s, CS + f * csrc_f, ps_csrc)) {
+            if (f == 0) return 1;                                   /* geometry not covered: nothing launched yet */
+            ctx->err = "frame group: front end refused frame"; return SRCNN_B200_ECUDA;
+        }
+        ctx->launches++;
+    }
+    st.mark(); st.skip(3);
+    if (launch_conv_tc(ctx->tc, Y16, g, p.ow, p.oh, Yp, p.r0, p.r1, ctx->num_sms, s, nullptr, G, yp_f)) {
+        ctx->err = std::string("conv_tc: ") + conv_tc_error(ctx->tc);
+        return SRCNN_B200_ECUDA;
+    }
+    ctx->launches++;
+    st.mark();
+    for (unsigned f = 0; f < G; f++) {
+        if (!launch_color_out_up(Yp + f * yp_f, CS + f * csrc_f, ps_csrc, p.w, p.s0, vc->view, hc->view, p.ow, p.r0, p.r1, p.d,
+                                 d_out + f * ob, d_conv ? d_conv + f * cb : nullptr, s)) {
+            ctx->err = "frame group: colour-out geometry not covered"; return SRCNN_B200_ECUDA;
+        }
+        ctx->launches++;
+    }
+    st.mark();
+    CK(cudaGetLastError());
+    ctx->last = p; ctx->have_last = false;                          /* (the plane getters describe single passes only) */
+    ctx->last_group = G;
     return 0;
 }
 
@@ -489,6 +563,7 @@ int srcnn_b200_create(int device, srcnn_b200_ctx** out)
     if (const char* e = getenv("SRCNN_B200_FUSE")) ctx->fuse_front = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_FUSE_COLOR")) ctx->fuse_color = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_CHROMA_UP")) ctx->chroma_up = atoi(e) != 0;
+    if (const char* e = getenv("SRCNN_B200_GROUP")) ctx->group_frames = atoi(e) != 0;
     {
         unsigned nt = std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2));
         if (const char* e = getenv("SRCNN_B200_COPY_THREADS")) nt = (unsigned)std::max(1, atoi(e));
@@ -784,6 +859,45 @@ int srcnn_b200_process_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w,
     return 0;
 }
 
+/* frames [f0, f0+G) of a batch, device-resident: the grouped route when it applies, run_pass per frame otherwise */
+static int batch_frames_device(srcnn_b200_ctx* ctx, unsigned w, unsigned h, unsigned d, float multiply, int filter, unsigned G,
+                               const uint8_t* d_src, uint8_t* d_out, uint8_t* d_conv)
+{
+    Plan p; int rc = make_plan(w, h, d, multiply, filter, 0, 1, p);
+    if (rc) return rc;
+    if ((rc = make_plan(w, h, d, multiply, filter, 0, p.oh, p))) return rc;
+    const size_t ib = (size_t)w * h * d, ob = (size_t)p.ow * p.oh * d, cb = (size_t)p.ow * p.oh;
+    if (G > 1) {
+        rc = run_group(ctx, p, G, d_src, d_out, d_conv);
+        if (rc <= 0) return rc;                                     /* done, or a real error; 1 = not covered */
+    }
+    for (unsigned f = 0; f < G; f++) {
+        Plan q; make_plan(w, h, d, multiply, filter, 0, p.oh, q);
+        if ((rc = run_pass(ctx, q, d_src + f * ib, 0, d_out + f * ob, d_conv ? d_conv + f * cb : nullptr))) return rc;
+    }
+    return 0;
+}
+
+int srcnn_b200_batch_device(srcnn_b200_ctx* ctx, const void* d_frames, unsigned n, unsigned w, unsigned h,
+                            unsigned d, float multiply, int filter, void* d_out, void* d_conv)
+{
+    if (!ctx || !d_frames || !d_out) return SRCNN_B200_EINVAL;
+    if (n == 0) return 0;
+    Plan p0; int rc = make_plan(w, h, d, multiply, filter, 0, 1, p0);
+    if (rc) return rc;
+    if ((rc = make_plan(w, h, d, multiply, filter, 0, p0.oh, p0))) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t ib = (size_t)w * h * d, ob = (size_t)p0.ow * p0.oh * d, cb = (size_t)p0.ow * p0.oh;
+    const unsigned G = group_size(ctx, p0, n);
+    for (unsigned f0 = 0; f0 < n; f0 += G) {
+        const unsigned g = std::min(G, n - f0);
+        rc = batch_frames_device(ctx, w, h, d, multiply, filter, g, static_cast<const uint8_t*>(d_frames) + f0 * ib,
+                                 static_cast<uint8_t*>(d_out) + f0 * ob, d_conv ? static_cast<uint8_t*>(d_conv) + f0 * cb : nullptr);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 int srcnn_b200_batch_host(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n, unsigned w, unsigned h,
                           unsigned d, float multiply, int filter, uint8_t* out, uint8_t* conv)
 {
@@ -791,29 +905,34 @@ int srcnn_b200_batch_host(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n
     if (n == 0) return 0;
     Plan p0; int rc = make_plan(w, h, d, multiply, filter, 0, 1, p0);
     if (rc) return rc;
+    if ((rc = make_plan(w, h, d, multiply, filter, 0, p0.oh, p0))) return rc;
     CK(cudaSetDevice(ctx->device));
     const size_t ib = (size_t)w * h * d, ob = (size_t)p0.ow * p0.oh * d, cb = (size_t)p0.ow * p0.oh;
+    /* frames per pipeline step (1 for large frames).  The host pipeline is bound by the download, and its fill / drain
+     * grow with the step size: at most 4 frames per step here (16 for device-resident batches) */
+    const unsigned G = std::min(4u, group_size(ctx, p0, n));
     for (int i = 0; i < 2; i++) {
-        CK(ctx->src8[i].ensure(ib)); CK(ctx->out8[i].ensure(ob));
-        if (conv) CK(ctx->conv8[i].ensure(cb));
+        CK(ctx->src8[i].ensure(ib * G)); CK(ctx->out8[i].ensure(ob * G));
+        if (conv) CK(ctx->conv8[i].ensure(cb * G));
     }
-    /* three-stage software pipeline over frames: upload (stream_in) | kernels (stream) | download (stream_out),
-     * double-buffered device input/output so frame i+1 uploads and frame i-1 downloads while frame i computes */
-    for (unsigned i = 0; i < n; i++) {
+    /* three-stage software pipeline over frame groups: upload (stream_in) | kernels (stream) | download (stream_out),
+     * double-buffered device input/output so group i+1 uploads and group i-1 downloads while group i computes */
+    unsigned i = 0;
+    for (unsigned f0 = 0; f0 < n; f0 += G, i++) {
+        const unsigned g = std::min(G, n - f0);
         const int b = (int)(i & 1);
-        if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream_in, ctx->ev_k[b], 0));      /* src8[b] consumed by frame i-2 */
-        CK(cudaMemcpyAsync(ctx->src8[b].p, frames + (size_t)i * ib, ib, cudaMemcpyHostToDevice, ctx->stream_in));
+        if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream_in, ctx->ev_k[b], 0));      /* src8[b] consumed by group i-2 */
+        CK(cudaMemcpyAsync(ctx->src8[b].p, frames + (size_t)f0 * ib, ib * g, cudaMemcpyHostToDevice, ctx->stream_in));
         CK(cudaEventRecord(ctx->ev_in[b], ctx->stream_in));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
-        if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));       /* out8[b] drained by frame i-2 */
-        Plan p; make_plan(w, h, d, multiply, filter, 0, p0.oh, p);
-        rc = run_pass(ctx, p, static_cast<const uint8_t*>(ctx->src8[b].p), 0, static_cast<uint8_t*>(ctx->out8[b].p),
-                      conv ? static_cast<uint8_t*>(ctx->conv8[b].p) : nullptr);
+        if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));       /* out8[b] drained by group i-2 */
+        rc = batch_frames_device(ctx, w, h, d, multiply, filter, g, static_cast<const uint8_t*>(ctx->src8[b].p),
+                                 static_cast<uint8_t*>(ctx->out8[b].p), conv ? static_cast<uint8_t*>(ctx->conv8[b].p) : nullptr);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_k[b], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->stream_out, ctx->ev_k[b], 0));
-        CK(cudaMemcpyAsync(out + (size_t)i * ob, ctx->out8[b].p, ob, cudaMemcpyDeviceToHost, ctx->stream_out));
-        if (conv) CK(cudaMemcpyAsync(conv + (size_t)i * cb, ctx->conv8[b].p, cb, cudaMemcpyDeviceToHost, ctx->stream_out));
+        CK(cudaMemcpyAsync(out + (size_t)f0 * ob, ctx->out8[b].p, ob * g, cudaMemcpyDeviceToHost, ctx->stream_out));
+        if (conv) CK(cudaMemcpyAsync(conv + (size_t)f0 * cb, ctx->conv8[b].p, cb * g, cudaMemcpyDeviceToHost, ctx->stream_out));
         CK(cudaEventRecord(ctx->ev_out[b], ctx->stream_out));
     }
     CK(cudaStreamSynchronize(ctx->stream_out));
@@ -858,6 +977,7 @@ int srcnn_b200_last_timings(srcnn_b200_ctx* ctx, float* ms7)
     memcpy(ms7, ctx->ms, sizeof(ctx->ms)); return 0;
 }
 unsigned long long srcnn_b200_launch_count(const srcnn_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+unsigned srcnn_b200_last_group(const srcnn_b200_ctx* ctx) { return ctx ? ctx->last_group : 0; }
 
 /* ---------------------------------------------------------------- single stages (parity tests) */
 

@@ -276,6 +276,37 @@ def test_batch_equals_per_frame(ctx, mode):
         assert np.array_equal(out[i], o) and np.array_equal(conv[i], c)
 
 
+@pytest.mark.parametrize("d,hw,filt,n", [(3, (64, 64), S.LANCZOS3, 7), (4, (40, 72), S.BICUBIC, 5), (3, (33, 50), S.BICUBIC, 3)])
+def test_frame_groups_equal_single_frames(ctx, d, hw, filt, n):
+    """batches of small frames run the fused convolution as ONE launch per group of frames (srcnn_b200_batch_host /
+    _batch_device): every frame must come out bit-identical to its own single pass (tensor mode included -- the FP32
+    sums do not depend on how rows are cut into work units), group sizes that do not divide the batch included"""
+    import os
+    import torch
+    h, w = hw
+    frames = np.stack([O.synth("uniform", h, w, d, 300 + i) for i in range(n)])
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    singles = [ctx.pass_host(frames[i], 2.0, filt, True) for i in range(n)]
+    out, conv = ctx.batch(frames, 2.0, filt, want_conv=True)
+    for i in range(n):
+        assert np.array_equal(out[i], singles[i][0]) and np.array_equal(conv[i], singles[i][1]), "host batch, frame %d" % i
+    d_src = torch.from_numpy(frames).cuda()
+    d_out = torch.zeros((n, 2 * h, 2 * w, d), dtype=torch.uint8, device="cuda")
+    d_conv = torch.zeros((n, 2 * h, 2 * w), dtype=torch.uint8, device="cuda")
+    ctx.batch_device(d_src.data_ptr(), n, w, h, d, 2.0, filt, d_out.data_ptr(), d_conv.data_ptr())
+    ctx.sync()
+    assert np.array_equal(d_out.cpu().numpy(), out) and np.array_equal(d_conv.cpu().numpy(), conv)
+    # and with grouping switched off (a context created with SRCNN_B200_GROUP=0)
+    os.environ["SRCNN_B200_GROUP"] = "0"
+    try:
+        c2 = S.Context(0, S.CONV_TENSOR)
+    finally:
+        os.environ.pop("SRCNN_B200_GROUP", None)
+    o2, cv2 = c2.batch(frames, 2.0, filt, want_conv=True)
+    c2.close()
+    assert np.array_equal(o2, out) and np.array_equal(cv2, conv)
+
+
 def test_device_resident_pass_equals_host_pass(ctx):
     import torch
     ctx.set_conv_mode(S.CONV_TENSOR)
