@@ -166,9 +166,15 @@ template <int D, bool CONV>
 __global__ void __launch_bounds__(256)
 color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc, size_t cstride, unsigned w, unsigned src_row0,
                     const int4* __restrict__ vpack, const int4* __restrict__ hpack,
-                    unsigned ow, unsigned row0, unsigned nrows, unsigned rpc, uint8_t* __restrict__ out, uint8_t* __restrict__ conv)
+                    unsigned ow, unsigned row0, unsigned nrows, unsigned rpc, uint8_t* __restrict__ out, uint8_t* __restrict__ conv,
+                    size_t yp_fstride, size_t csrc_fstride, size_t out_fstride, size_t conv_fstride)
 {
     constexpr int NC = D - 1;
+    if (gridDim.z > 1) {                              /* frame group: this CTA's frame */
+        yp += (size_t)blockIdx.z * yp_fstride; csrc += (size_t)blockIdx.z * csrc_fstride;
+        out += (size_t)blockIdx.z * out_fstride;
+        if (CONV) conv += (size_t)blockIdx.z * conv_fstride;
+    }
     /* the intermediate (vertically resampled) plane: every WARP stages the source columns of its own 128 pixels (so rows
      * need only __syncwarp, warps run independently), double-buffered by row parity */
     __shared__ float tS[8][2][NC][kUpMaxCols];
@@ -263,12 +269,15 @@ bool color_out_up_quads_ok(const int* h_hcl, unsigned ow)
 
 bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, unsigned w, unsigned src_row0,
                          const AxisTableDev& vc, const AxisTableDev& hc, unsigned ow, unsigned row0, unsigned row1, unsigned d,
-                         uint8_t* out, uint8_t* conv, cudaStream_t s)
+                         uint8_t* out, uint8_t* conv, cudaStream_t s,
+                         unsigned nframes, size_t yp_fstride, size_t csrc_fstride, size_t out_fstride, size_t conv_fstride)
 {
     auto al = [](const void* p, unsigned a) { return ((uintptr_t)p % a) == 0; };
+    if (nframes == 0) nframes = 1;
+    if (nframes > 1 && ((yp_fstride % 4) || (out_fstride % 16) || (conv && (conv_fstride % 4)))) return false;
     if (!vc.pack2 || !hc.pack2 || (ow % 4) || row1 <= row0) return false;
     if (!al(yp, 16) || !al(out, d == 4 ? 16 : 4) || (conv && !al(conv, 4))) return false;
-    const unsigned gx = (ow + kUpBlockPx - 1) / kUpBlockPx, nrows = row1 - row0;
+    const unsigned gx = (ow + kUpBlockPx - 1) / kUpBlockPx * nframes, nrows = row1 - row0;   /* (x nframes: for the wave estimate) */
     /* rows per CTA: 4 CTAs of 64-72 registers x 256 threads are resident per SM; pick the row count that minimises
      * (number of waves) x (rows + one row-time of prologue), i.e. avoids a nearly empty last wave */
     static int sms = 0;
@@ -279,10 +288,10 @@ bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, uns
         const size_t cost = waves * (r + 1);
         if (cost <= best) { best = cost; rpc = r; }
     }
-    dim3 grid(gx, (nrows + rpc - 1) / rpc);
-    if (grid.y > 65535u) return false;
+    dim3 grid(gx / nframes, (nrows + rpc - 1) / rpc, nframes);
+    if (grid.y > 65535u || grid.z > 65535u) return false;
 #define SRCNN_COU(D_, C_) color_out_up_kernel<D_, C_><<<grid, 256, 0, s>>>(yp, csrc, cstride, w, src_row0, \
-        reinterpret_cast<const int4*>(vc.pack2), reinterpret_cast<const int4*>(hc.pack2), ow, row0, nrows, rpc, out, conv)
+        reinterpret_cast<const int4*>(vc.pack2), reinterpret_cast<const int4*>(hc.pack2), ow, row0, nrows, rpc, out, conv, yp_fstride, csrc_fstride, out_fstride, conv_fstride)
     if (d == 4) { if (conv) SRCNN_COU(4, true); else SRCNN_COU(4, false); }
     else        { if (conv) SRCNN_COU(3, true); else SRCNN_COU(3, false); }
 #undef SRCNN_COU

@@ -65,10 +65,13 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
                 __half* y16, Y16Geom g, unsigned strip_row0,
                 const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc,
                 const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, cudaStream_t s,
-                float* csrc = nullptr, size_t csrc_stride = 0);
+                float* csrc = nullptr, size_t csrc_stride = 0,
+                unsigned nframes = 1, size_t src_fstride = 0, size_t y16_fstride = 0, size_t csrc_fstride = 0);
 /* csrc (optional, honoured only when the chroma tables are "pow2pair"): Cb / Cr / A are NOT resampled; their colour-converted
  * FP32 samples are stored at source resolution, plane k at csrc + k * csrc_stride, row 0 = source row src_row0, pitch w,
- * for launch_color_out_up to resample.  prep_chroma_handover() tells whether a set of tables takes that route. */
+ * for launch_color_out_up to resample.  prep_chroma_handover() tells whether a set of tables takes that route.
+ * nframes > 1 (hand-over route only): a group of same-geometry frames in one launch, frame f at src + f * src_fstride (bytes),
+ * y16 + f * y16_fstride (halves), csrc + f * csrc_fstride (floats). */
 bool prep_chroma_handover(const AxisTableDev& vc, const AxisTableDev& hc);
 /* host-side applicability test of launch_prep for a set of tables */
 bool prep_supported(const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc);
@@ -111,7 +114,9 @@ const char* conv_tc_error(const ConvTcState* st);
  * [row0,row1) of the strip.  Returns false (nothing launched) if the geometry is not covered. */
 bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, unsigned w, unsigned src_row0,
                          const AxisTableDev& vc, const AxisTableDev& hc, unsigned ow, unsigned row0, unsigned row1, unsigned d,
-                         uint8_t* out, uint8_t* conv, cudaStream_t s);
+                         uint8_t* out, uint8_t* conv, cudaStream_t s,
+                         unsigned nframes = 1, size_t yp_fstride = 0, size_t csrc_fstride = 0, size_t out_fstride = 0,
+                         size_t conv_fstride = 0);
 /* host-side: the source columns any CTA of that kernel reads fit its shared-memory row (h_hcl = compact lefts of the table) */
 bool color_out_up_quads_ok(const int* h_hcl, unsigned ow);
 void launch_color_out(const float* yprime, const float* cb, const float* cr, const float* a, size_t npix,

@@ -60,6 +60,8 @@ struct PrepParams {
      * colour-converted FP32 samples of the footprint are written to csrc[plane][(row - src_row0) * w + col] and the x2
      * colour-out kernel (color.cu: color_out_up_kernel) resamples them on the fly -- 4 x less chroma traffic */
     float* csrc; size_t csrc_stride;
+    /* frame groups (gridDim.z = frames of identical geometry): byte / element distance between consecutive frames */
+    size_t src_fstride, y16_fstride, csrc_fstride;
 };
 
 __device__ __forceinline__ void ycbcr_of(float r, float g, float b, float& y, float& cb, float& cr)
@@ -182,6 +184,10 @@ template <int D, int WY, int WC, int CM, int SC>
 __global__ void __launch_bounds__(NT)
 prep_kernel(const PrepParams p)
 {
+    /* frame group (gridDim.z > 1): this CTA's frame */
+    const uint8_t* const f_src = p.src + (size_t)blockIdx.z * p.src_fstride;
+    __half* const f_y16 = p.y16 ? p.y16 + (size_t)blockIdx.z * p.y16_fstride : nullptr;
+    float* const f_csrc = p.csrc ? p.csrc + (size_t)blockIdx.z * p.csrc_fstride : nullptr;
     constexpr bool CFMA = (CM == 1);
     constexpr bool C32 = (CM == 2);                   /* chroma / alpha as interleaved FP32 (pow2pair tables) */
     constexpr int NC = D - 1;
@@ -234,7 +240,7 @@ prep_kernel(const PrepParams p)
         const int pl = SR * SC;
         #pragma unroll 1
         for (int r = warp; r < nr; r += NW) {
-            const uint8_t* row = p.src + ((size_t)(rlo + r - (int)p.src_row0) * p.w + (size_t)clo) * D;
+            const uint8_t* row = f_src + ((size_t)(rlo + r - (int)p.src_row0) * p.w + (size_t)clo) * D;
             double* s = S + r * SC;
             #pragma unroll 1
             for (int cb = 0; cb < nc; cb += 96) {
@@ -252,9 +258,9 @@ prep_kernel(const PrepParams p)
                     ycbcr_of((float)v[k][0], (float)v[k][1], (float)v[k][2], y, cb_, cr);
                     if (c < nc) {
                         s[c] = (double)y;
-                        if (C32 && p.csrc) {
+                        if (C32 && f_csrc) {
                             /* neighbouring tiles' footprints overlap: they store identical values (benign) */
-                            float* q = p.csrc + (size_t)(rlo + r - (int)p.src_row0) * p.w + (size_t)(clo + c);
+                            float* q = f_csrc + (size_t)(rlo + r - (int)p.src_row0) * p.w + (size_t)(clo + c);
                             q[0] = cb_; q[p.csrc_stride] = cr;
                             if (NC == 3) q[2 * p.csrc_stride] = (float)v[k][D - 1];
                         } else if (C32) {
@@ -282,7 +288,7 @@ prep_kernel(const PrepParams p)
         const double* t = T + rbeg * SC + (hly - clo);
         float* o32 = p.planes + (size_t)(gy0 + rbeg - p.e0) * p.ow + gx;
         /* conv input: FP16 (RN), plane column = image column + 8 */
-        __half* o16 = p.y16 ? p.y16 + (size_t)(ybase + rbeg) * p.pitch + gx + kY16PadL : nullptr;
+        __half* o16 = f_y16 ? f_y16 + (size_t)(ybase + rbeg) * p.pitch + gx + kY16PadL : nullptr;
         const unsigned ow = p.ow; const int pitch = p.pitch;
         if (o16 && !p.write_y32)
             hpass<WY, false, SC>(t, wy, nrows, [&](int r, float v) { o16[r * pitch] = __float2half_rn(v); });
@@ -297,14 +303,14 @@ prep_kernel(const PrepParams p)
     /* 2b. replicate padding of the conv-input plane around the image (only border tiles do any work):
      * columns 0..7 repeat image column 0, columns ow+8..pitch-1 repeat column ow-1, the rows above / below the image
      * repeat row 0 / oh-1 -- conv I clamps Y coordinates (src/libsrcnn.cpp:362-392) */
-    if (p.y16) {
+    if (f_y16) {
         const bool first_col = (x0 == 0), last_col = (x0 + nx == p.ow);
         if (first_col || last_col) {
             const int c_hi = (int)p.ow + kY16PadL, npad_r = last_col ? p.pitch - c_hi : 0, npad_l = first_col ? kY16PadL : 0;
             const int per_row = npad_l + npad_r;
             for (int idx = tid; idx < ny * per_row; idx += NT) {
                 const int r = idx / per_row, k = idx - r * per_row;
-                __half* row = p.y16 + (size_t)(ybase + r) * p.pitch;
+                __half* row = f_y16 + (size_t)(ybase + r) * p.pitch;
                 if (k < npad_l) row[k] = row[kY16PadL];
                 else            row[c_hi + (k - npad_l)] = row[c_hi - 1];
             }
@@ -316,25 +322,25 @@ prep_kernel(const PrepParams p)
             const int ca = first_col ? 0 : (int)x0 + kY16PadL, cb = last_col ? p.pitch : (int)x0 + nx + kY16PadL;
             const int span = cb - ca;
             if (top) {
-                const __half* from = p.y16 + (size_t)ybase * p.pitch + ca;
+                const __half* from = f_y16 + (size_t)ybase * p.pitch + ca;
                 for (int idx = tid; idx < ybase * span; idx += NT) {
                     const int r = idx / span, c = idx - r * span;
-                    p.y16[(size_t)r * p.pitch + ca + c] = from[c];
+                    f_y16[(size_t)r * p.pitch + ca + c] = from[c];
                 }
             }
             if (bottom) {
                 const int rb = ybase + ny, nrep = p.y16_rows - rb;
-                const __half* from = p.y16 + (size_t)(rb - 1) * p.pitch + ca;
+                const __half* from = f_y16 + (size_t)(rb - 1) * p.pitch + ca;
                 for (int idx = tid; idx < nrep * span; idx += NT) {
                     const int r = idx / span, c = idx - r * span;
-                    p.y16[(size_t)(rb + r) * p.pitch + ca + c] = from[c];
+                    f_y16[(size_t)(rb + r) * p.pitch + ca + c] = from[c];
                 }
             }
         }
     }
 
     /* 3. planes 1 .. D-1 (Cb, Cr, A): bilinear / box tables */
-    if (C32 && p.csrc) {
+    if (C32 && f_csrc) {
         /* handed over at source resolution (colour-in above) */
     } else if (C32) {
         float* Tc = reinterpret_cast<float*>(T);
@@ -464,8 +470,9 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
                 __half* y16, Y16Geom g, unsigned strip_row0,
                 const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc,
                 const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, cudaStream_t s,
-                float* csrc, size_t csrc_stride)
+                float* csrc, size_t csrc_stride, unsigned nframes, size_t src_fstride, size_t y16_fstride, size_t csrc_fstride)
 {
+    if (nframes > 1 && (planes || write_y32 || !csrc)) return 0;     /* groups: the x2 hand-over route only */
     if (!prep_supported(vy, vc, hy, hc) || (d != 3 && d != 4)) return 0;
     PrepParams p;
     p.src = src; p.w = w; p.src_row0 = src_row0; p.ow = ow; p.oh = oh; p.e0 = e0; p.e1 = e1;
@@ -478,11 +485,13 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
     /* chroma arithmetic: 2 = FP32 two-tap (pow2pair tables), 1 = FP64 fused multiply-add (exact29), 0 = FP64 mul + add */
     const int cm = (vc.pow2pair && hc.pow2pair && !getenv_flag("SRCNN_B200_PREP_F64")) ? 2 : (vc.exact29 && hc.exact29) ? 1 : 0;
     if (cm != 2) csrc = nullptr;
+    if (nframes > 1 && !csrc) return 0;
     p.csrc = csrc; p.csrc_stride = csrc_stride;
+    p.src_fstride = src_fstride; p.y16_fstride = y16_fstride; p.csrc_fstride = csrc_fstride;
     if (prep_smem((int)d, cm, p.SR, 104, csrc != nullptr) > 160 * 1024) return 0;
     if ((size_t)oh * 8 >= (size_t)INT_MAX || (size_t)ow * 8 >= (size_t)INT_MAX) return 0;
-    dim3 grid((ow + TW - 1) / TW, (e1 - e0 + TH - 1) / TH);
-    if (grid.y > 65535u) return 0;
+    dim3 grid((ow + TW - 1) / TW, (e1 - e0 + TH - 1) / TH, nframes ? nframes : 1);
+    if (grid.y > 65535u || grid.z > 65535u) return 0;
     return d == 3 ? launch_d<3>(p, vy.cwin, cm, grid, s) : launch_d<4>(p, vy.cwin, cm, grid, s);
 }
 

@@ -497,15 +497,11 @@ int run_group(srcnn_b200_ctx* ctx, Plan& p, unsigned G, const uint8_t* d_src, ui
     float* Yp = static_cast<float*>(ctx->yprime.p);
     cudaStream_t s = ctx->stream;
     Stamp st(ctx);                                                  /* timings then describe the whole group */
-    for (unsigned f = 0; f < G; f++) {
-        if (!launch_prep(d_src + f * ib + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, 0, false,
-                         Y16 + f * y16_f, g, p.r0, vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(),
-                         vc->host.cleft.data(), hy->host.cleft.data(), hc->host.cleft.data(), s, CS + f * csrc_f, ps_csrc)) {
-            if (f == 0) return 1;                                   /* geometry not covered: nothing launched yet */
-            ctx->err = "frame group: front end refused frame"; return SRCNN_B200_ECUDA;
-        }
-        ctx->launches++;
-    }
+    if (!launch_prep(d_src + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, 0, false,
+                     Y16, g, p.r0, vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(),
+                     vc->host.cleft.data(), hy->host.cleft.data(), hc->host.cleft.data(), s, CS, ps_csrc,
+                     G, ib, y16_f, csrc_f)) return 1;                /* geometry not covered: nothing launched */
+    ctx->launches++;
     st.mark(); st.skip(3);
     if (launch_conv_tc(ctx->tc, Y16, g, p.ow, p.oh, Yp, p.r0, p.r1, ctx->num_sms, s, nullptr, G, yp_f)) {
         ctx->err = std::string("conv_tc: ") + conv_tc_error(ctx->tc);
@@ -513,13 +509,11 @@ int run_group(srcnn_b200_ctx* ctx, Plan& p, unsigned G, const uint8_t* d_src, ui
     }
     ctx->launches++;
     st.mark();
-    for (unsigned f = 0; f < G; f++) {
-        if (!launch_color_out_up(Yp + f * yp_f, CS + f * csrc_f, ps_csrc, p.w, p.s0, vc->view, hc->view, p.ow, p.r0, p.r1, p.d,
-                                 d_out + f * ob, d_conv ? d_conv + f * cb : nullptr, s)) {
-            ctx->err = "frame group: colour-out geometry not covered"; return SRCNN_B200_ECUDA;
-        }
-        ctx->launches++;
+    if (!launch_color_out_up(Yp, CS, ps_csrc, p.w, p.s0, vc->view, hc->view, p.ow, p.r0, p.r1, p.d, d_out, d_conv, s,
+                             G, yp_f, csrc_f, ob, cb)) {
+        ctx->err = "frame group: colour-out geometry not covered"; return SRCNN_B200_ECUDA;
     }
+    ctx->launches++;
     st.mark();
     CK(cudaGetLastError());
     ctx->last = p; ctx->have_last = false;                          /* (the plane getters describe single passes only) */
