@@ -4,6 +4,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <exception>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -40,6 +41,7 @@ bool decode_png(const unsigned char* data, size_t n, Image& img, std::string& er
         const unsigned char* tag = data + pos + 4;
         const unsigned char* body = data + pos + 8;
         if ((size_t)len > n - pos - 12) { err = "PNG: truncated chunk"; return false; }
+        if ((unsigned)crc32(0L, tag, (uInt)len + 4) != be32(body + len)) { err = "PNG: chunk CRC mismatch (corrupt file)"; return false; }
         if (!memcmp(tag, "IHDR", 4) && len >= 13) {
             w = be32(body); h = be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12];
             have_ihdr = true;
@@ -62,7 +64,7 @@ bool decode_png(const unsigned char* data, size_t n, Image& img, std::string& er
     if (ctype == 3 && (depth == 16 || plte.size() < 3)) { err = "PNG: bad palette image"; return false; }
     const size_t bpp = (ch * depth + 7) / 8;                     /* filter distance in bytes */
     const size_t stride = ((size_t)w * ch * depth + 7) / 8;
-    if (stride == 0 || (size_t)h > (size_t)-1 / (stride + 1)) { err = "PNG: image too large"; return false; }
+    if (stride == 0 || (size_t)h > ((size_t)1 << 34) / (stride + 1)) { err = "PNG: image too large"; return false; }   /* 16 GiB of raw scanlines */
     std::vector<unsigned char> raw((stride + 1) * (size_t)h);
     {
         z_stream zs; memset(&zs, 0, sizeof zs);
@@ -220,12 +222,17 @@ bool read_file(const std::string& path, std::vector<unsigned char>& out)
 
 bool decode(const unsigned char* data, size_t n, Image& img, std::string& err)
 {
-    switch (sniff(data, n)) {
-        case T_PNG: return decode_png(data, n, img, err);
-        case T_BMP: return decode_bmp(data, n, img, err);
-        case T_PNM: return decode_pnm(data, n, img, err);
-        case T_JPEG: err = "JPEG decoding is not built in; convert the file to PNG first"; return false;
-        default: err = "unknown image format"; return false;
+    try {
+        switch (sniff(data, n)) {
+            case T_PNG: return decode_png(data, n, img, err);
+            case T_BMP: return decode_bmp(data, n, img, err);
+            case T_PNM: return decode_pnm(data, n, img, err);
+            case T_JPEG: err = "JPEG decoding is not built in; convert the file to PNG first"; return false;
+            default: err = "unknown image format"; return false;
+        }
+    } catch (const std::exception& e) {          /* std::bad_alloc / length_error on absurd dimensions */
+        err = std::string("out of memory while decoding (") + e.what() + ")";
+        return false;
     }
 }
 

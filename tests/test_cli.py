@@ -105,6 +105,32 @@ def test_rejects_garbage_and_jpeg(tmp_path):
     assert _run(CLI).returncode != 0                                         # no arguments: usage, non-zero
 
 
+def test_corrupt_and_truncated_png_are_rejected_cleanly(tmp_path):
+    """damaged files must produce an error message and a non-zero exit code, never a crash or a bogus image"""
+    _need_cli()
+    good = tmp_path / "good.png"
+    Image.fromarray(_rng_img(40, 60, 3, 9)).save(good)
+    raw = good.read_bytes()
+    cases = {
+        "cut_in_idat": raw[: len(raw) // 2],
+        "cut_after_sig": raw[:8],
+        "bad_zlib": raw[:60] + bytes(b ^ 0x5A for b in raw[60:120]) + raw[120:],
+        "huge_dims": raw[:16] + (0x7FFFFFFF).to_bytes(4, "big") + (0x7FFFFFFF).to_bytes(4, "big") + raw[24:],
+        "empty": b"",
+    }
+    import struct, zlib
+    ihdr = struct.pack(">IIBBBBB", 0x7FFFFFFF, 0x7FFFFFFF, 8, 2, 0, 0, 0)      # absurd size, VALID chunk CRCs
+    def chunk(t, b):
+        return struct.pack(">I", len(b)) + t + b + struct.pack(">I", zlib.crc32(t + b))
+    cases["huge_dims_valid_crc"] = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+    for name, data in cases.items():
+        p = tmp_path / (name + ".png")
+        p.write_bytes(data)
+        r = _run(CLI, p, "--decode-only", tmp_path / "o.png")
+        assert r.returncode not in (0, -11, 139), "%s: rc %s\n%s" % (name, r.returncode, r.stdout + r.stderr)
+        assert "Failed to load image" in r.stdout, name
+
+
 def test_default_output_names_follow_the_reference(tmp_path):
     """<src>_resized.png next to the source when no output name is given (src/test.cpp:385-411)"""
     _need_cli()
