@@ -8,6 +8,7 @@
  * (its x86-64 -O2 build has no FMA contraction), so both kernels are bit-exact against the oracle.
  */
 #include "kernels.h"
+#include <cstdlib>
 #include "color_math.cuh"
 
 namespace srcnn {
@@ -170,6 +171,7 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
                     size_t yp_fstride, size_t csrc_fstride, size_t out_fstride, size_t conv_fstride)
 {
     constexpr int NC = D - 1;
+    pdl_wait();                                       /* Y' comes from the conv kernel this launch may overlap with */
     if (gridDim.z > 1) {                              /* frame group: this CTA's frame */
         yp += (size_t)blockIdx.z * yp_fstride; csrc += (size_t)blockIdx.z * csrc_fstride;
         out += (size_t)blockIdx.z * out_fstride;
@@ -256,6 +258,13 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
 }
 
 /* host-side: the source columns one warp (kUpWarpPx output pixels) reads fit its shared-memory row, and lefts are monotonic */
+bool pdl_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SRCNN_B200_PDL"); on = (e && *e == '0') ? 0 : 1; }
+    return on != 0;
+}
+
 bool color_out_up_quads_ok(const int* h_hcl, unsigned ow)
 {
     if (ow % 4) return false;
@@ -290,7 +299,7 @@ bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, uns
     }
     dim3 grid(gx / nframes, (nrows + rpc - 1) / rpc, nframes);
     if (grid.y > 65535u || grid.z > 65535u) return false;
-#define SRCNN_COU(D_, C_) color_out_up_kernel<D_, C_><<<grid, 256, 0, s>>>(yp, csrc, cstride, w, src_row0, \
+#define SRCNN_COU(D_, C_) launch_pdl(color_out_up_kernel<D_, C_>, grid, dim3(256), 0, s, yp, csrc, cstride, w, src_row0, \
         reinterpret_cast<const int4*>(vc.pack2), reinterpret_cast<const int4*>(hc.pack2), ow, row0, nrows, rpc, out, conv, yp_fstride, csrc_fstride, out_fstride, conv_fstride)
     if (d == 4) { if (conv) SRCNN_COU(4, true); else SRCNN_COU(4, false); }
     else        { if (conv) SRCNN_COU(3, true); else SRCNN_COU(3, false); }

@@ -355,6 +355,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     __syncthreads();
     tc_fence_after();
 
+    /* everything above touched only the (constant) weight image; from here on the conv-input plane of the front end is read
+     * and Y' is written: wait for the preceding kernel if this is a programmatic dependent launch, then let the colour-out
+     * kernel be scheduled as soon as CTAs of this grid retire */
+    pdl_wait();
+    pdl_launch_dependents();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + S_TMEM);
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);     /* this warp's TMEM lane quarter */
     const Span span = span_of(p);
@@ -887,7 +892,7 @@ int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, u
     p.prof = d_prof;
 #endif
     if (p.rgb) conv_tc_kernel<true><<<grid, NWARPS * 32, SMEM_BYTES, s>>>(p, map);
-    else       conv_tc_kernel<false><<<grid, NWARPS * 32, SMEM_BYTES, s>>>(p, map);
+    else       launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(NWARPS * 32), SMEM_BYTES, s, p, map);
 #ifdef SRCNN_PROF
     {
         cudaStreamSynchronize(s);

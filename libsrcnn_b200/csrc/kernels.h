@@ -9,6 +9,28 @@
 
 namespace srcnn {
 
+/* Programmatic dependent launch (PDL): a kernel launched with launch_pdl may start while the previous kernel of the stream is
+ * still draining -- its prologue (weight staging, barrier / tensor-memory set-up, index arithmetic) overlaps the predecessor's
+ * tail.  Contract: the predecessor executes pdl_launch_dependents() (any time), the dependent executes pdl_wait() before its
+ * first access to memory the predecessor writes.  Both are no-ops in a normally launched kernel.  SRCNN_B200_PDL=0 turns the
+ * attribute off. */
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 /* per-axis contribution table on the device (built on the host in double, contrib.cpp) */
 struct AxisTableDev {
     const int*    left;     /* [dst]  first source index           */

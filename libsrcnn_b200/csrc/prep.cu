@@ -184,6 +184,7 @@ template <int D, int WY, int WC, int CM, int SC>
 __global__ void __launch_bounds__(NT)
 prep_kernel(const PrepParams p)
 {
+    pdl_launch_dependents();                          /* the conv kernel may set itself up while this grid drains */
     /* frame group (gridDim.z > 1): this CTA's frame */
     const uint8_t* const f_src = p.src + (size_t)blockIdx.z * p.src_fstride;
     __half* const f_y16 = p.y16 ? p.y16 + (size_t)blockIdx.z * p.y16_fstride : nullptr;
