@@ -171,7 +171,6 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
                     size_t yp_fstride, size_t csrc_fstride, size_t out_fstride, size_t conv_fstride)
 {
     constexpr int NC = D - 1;
-    pdl_wait();                                       /* Y' comes from the conv kernel this launch may overlap with */
     if (gridDim.z > 1) {                              /* frame group: this CTA's frame */
         yp += (size_t)blockIdx.z * yp_fstride; csrc += (size_t)blockIdx.z * csrc_fstride;
         out += (size_t)blockIdx.z * out_fstride;
@@ -214,6 +213,9 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
         }
         if (active) py = __ldg(reinterpret_cast<const float4*>(yp + (size_t)ry * ow + x0));
     };
+    /* up to here only constant tables were read: as a programmatic dependent launch this much overlaps the conv kernel's
+     * tail; Y' (and, two kernels back, the chroma samples) is read from here on */
+    pdl_wait();
     if (ry0 < ry1) prefetch(ry0);
     for (unsigned ry = ry0; ry < ry1; ry++) {
         float (*t)[kUpMaxCols] = tS[wq][ry & 1];
