@@ -262,9 +262,8 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
 /* host-side: the source columns one warp (kUpWarpPx output pixels) reads fit its shared-memory row, and lefts are monotonic */
 bool pdl_enabled()
 {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("SRCNN_B200_PDL"); on = (e && *e == '0') ? 0 : 1; }
-    return on != 0;
+    static const bool on = [] { const char* e = getenv("SRCNN_B200_PDL"); return !(e && *e == '0'); }();   /* thread-safe once */
+    return on;
 }
 
 bool color_out_up_quads_ok(const int* h_hcl, unsigned ow)
@@ -280,7 +279,7 @@ bool color_out_up_quads_ok(const int* h_hcl, unsigned ow)
 
 bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, unsigned w, unsigned src_row0,
                          const AxisTableDev& vc, const AxisTableDev& hc, unsigned ow, unsigned row0, unsigned row1, unsigned d,
-                         uint8_t* out, uint8_t* conv, cudaStream_t s,
+                         uint8_t* out, uint8_t* conv, cudaStream_t s, int num_sms,
                          unsigned nframes, size_t yp_fstride, size_t csrc_fstride, size_t out_fstride, size_t conv_fstride)
 {
     auto al = [](const void* p, unsigned a) { return ((uintptr_t)p % a) == 0; };
@@ -291,8 +290,7 @@ bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, uns
     const unsigned gx = (ow + kUpBlockPx - 1) / kUpBlockPx * nframes, nrows = row1 - row0;   /* (x nframes: for the wave estimate) */
     /* rows per CTA: 4 CTAs of 64-72 registers x 256 threads are resident per SM; pick the row count that minimises
      * (number of waves) x (rows + one row-time of prologue), i.e. avoids a nearly empty last wave */
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148; }
+    const int sms = num_sms > 0 ? num_sms : 148;
     unsigned rpc = 2; size_t best = ~(size_t)0;
     for (unsigned r = 2; r <= (unsigned)kUpRowsMax; r++) {
         const size_t ctas = (size_t)gx * ((nrows + r - 1) / r), waves = (ctas + (size_t)sms * 4 - 1) / ((size_t)sms * 4);

@@ -13,6 +13,7 @@
  * with the reference's coordinate clamping.
  */
 #include "kernels.h"
+#include <atomic>
 #include "srcnn_weights_data.h"
 
 namespace srcnn {
@@ -124,7 +125,13 @@ void launch_conv_exact(const float* y, unsigned dw, unsigned dh, unsigned win_ro
                        float* out, unsigned row0, unsigned row1, cudaStream_t s)
 {
     const size_t smem = (size_t)(YT * YT + 32 * L2P) * sizeof(float);
-    cudaFuncSetAttribute(conv_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    /* the opt-in is a per-device function attribute: set it once per device, not on every launch */
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !configured[dev].load(std::memory_order_acquire)) {
+        if (cudaFuncSetAttribute(conv_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
+            configured[dev].store(true, std::memory_order_release);
+    }
     dim3 grid((dw + TILE - 1) / TILE, (row1 - row0 + TILE - 1) / TILE);
     conv_exact_kernel<<<grid, 256, smem, s>>>(y, (int)dw, (int)dh, (int)win_row0, (int)(win_row0 + win_rows), out, (int)row0, (int)row1);
 }

@@ -81,7 +81,7 @@ void launch_resize_horizontal(const float* in, size_t in_plane_stride, unsigned 
  * upscale order (vertical pass first) with compact tables.  src = device pointer at source row src_row0; planes = d FP32
  * planes whose row 0 is destination row e0 (plane 0 only written if write_y32); y16 may be NULL (no conv-input plane).
  * h_* = the host copies of the compact `left` arrays (tile footprints).  Returns 1 if launched, 0 if this geometry is
- * not covered (the caller then runs the separate kernels). */
+ * not covered (the caller then runs the separate kernels), -1 if the launch itself failed. */
 int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, unsigned ow, unsigned oh,
                 unsigned e0, unsigned e1, float* planes, size_t plane_stride, bool write_y32,
                 __half* y16, Y16Geom g, unsigned strip_row0,
@@ -107,7 +107,8 @@ void launch_pack_y16(const float* y, unsigned dw, unsigned dh, unsigned win_row0
  * y: window rows [win_row0, ...) of the dw x dh interpolated plane; out: rows [row0,row1) x dw */
 void launch_conv_exact(const float* y, unsigned dw, unsigned dh, unsigned win_row0, unsigned win_rows,
                        float* out, unsigned row0, unsigned row1, cudaStream_t s);
-int  conv_exact_init();    /* uploads the FP32 parameter tables to __constant__ memory of the current device */
+int  conv_exact_init();    /* current device: uploads the FP32 parameter tables to __constant__ memory, opts the kernel in to its
+                              dynamic shared memory size */
 
 /* fused conv I+II+III, tcgen05 / TMEM / TMA path (product mode) -- conv_tc.cu */
 struct ConvTcState;                         /* per-context: device weights image, tensor maps */
@@ -136,7 +137,7 @@ const char* conv_tc_error(const ConvTcState* st);
  * [row0,row1) of the strip.  Returns false (nothing launched) if the geometry is not covered. */
 bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, unsigned w, unsigned src_row0,
                          const AxisTableDev& vc, const AxisTableDev& hc, unsigned ow, unsigned row0, unsigned row1, unsigned d,
-                         uint8_t* out, uint8_t* conv, cudaStream_t s,
+                         uint8_t* out, uint8_t* conv, cudaStream_t s, int num_sms,
                          unsigned nframes = 1, size_t yp_fstride = 0, size_t csrc_fstride = 0, size_t out_fstride = 0,
                          size_t conv_fstride = 0);
 /* host-side: the source columns any CTA of that kernel reads fit its shared-memory row (h_hcl = compact lefts of the table) */

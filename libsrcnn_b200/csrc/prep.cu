@@ -32,6 +32,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <cstdlib>
 
@@ -393,18 +394,24 @@ inline size_t prep_smem(int d, int cm, int SR, int SC, bool csrc)
     return ((size_t)d * SR + TH) * SC * sizeof(double);
 }
 
+/* Function attributes are per device: every prep_kernel instantiation keeps one "opted in to large dynamic shared memory"
+ * flag per CUDA device (contexts on several GPUs of one process, srcnn_b200_multi). */
+constexpr int kMaxDevices = 64;
+
 template <int D, int WY, int WC, int CM, int SC>
 int launch_one(const PrepParams& p, dim3 grid, cudaStream_t s)
 {
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<bool> configured[kMaxDevices];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return 0; }
+    if (!configured[dev].load(std::memory_order_acquire)) {
         if (cudaFuncSetAttribute(prep_kernel<D, WY, WC, CM, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
             cudaGetLastError(); return 0;
         }
-        configured = true;
+        configured[dev].store(true, std::memory_order_release);
     }
     prep_kernel<D, WY, WC, CM, SC><<<grid, NT, prep_smem(D, CM, p.SR, SC, p.csrc != nullptr), s>>>(p);
-    return 1;
+    return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;      /* -1: the launch itself failed (sticky error left for the caller) */
 }
 
 /* shared-memory row pitch (doubles): 72 covers magnifications >= 2 (128/2 + window), 104 those >= 1.5 */

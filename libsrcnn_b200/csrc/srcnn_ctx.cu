@@ -344,11 +344,13 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
                     hc->quads_ok && ((uintptr_t)d_out % (p.d == 4 ? 16 : 4)) == 0 &&
                     (!d_conv || ((uintptr_t)d_conv % 4) == 0);
         if (chroma_up) CK(ctx->chroma_src.ensure(ps_csrc * (p.d - 1) * sizeof(float)));
-        fused = launch_prep(d_src, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, P_dst, ps_dst, y32,
-                            tensor ? static_cast<__half*>(ctx->y16.p) : nullptr, g, p.r0,
-                            vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
-                            hy->host.cleft.data(), hc->host.cleft.data(), s,
-                            chroma_up ? static_cast<float*>(ctx->chroma_src.p) : nullptr, ps_csrc) != 0;
+        const int lp = launch_prep(d_src, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, P_dst, ps_dst, y32,
+                                   tensor ? static_cast<__half*>(ctx->y16.p) : nullptr, g, p.r0,
+                                   vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
+                                   hy->host.cleft.data(), hc->host.cleft.data(), s,
+                                   chroma_up ? static_cast<float*>(ctx->chroma_src.p) : nullptr, ps_csrc);
+        if (lp < 0) return fail_cuda(ctx, cudaGetLastError(), "prep_kernel launch");
+        fused = lp != 0;
         if (!fused) chroma_up = false;
     }
     ctx->last_has_chroma = !chroma_up;
@@ -425,7 +427,7 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
     /* 6. colour-out (+ conv plane) for the strip rows, unless the conv kernel already stored them */
     if (!fuse_out && chroma_up) {
         if (!launch_color_out_up(Yp, static_cast<const float*>(ctx->chroma_src.p), ps_csrc, p.w, p.s0, vc->view, hc->view,
-                                 p.ow, p.r0, p.r1, p.d, d_out, d_conv, s)) {
+                                 p.ow, p.r0, p.r1, p.d, d_out, d_conv, s, ctx->num_sms)) {
             ctx->err = "colour-out (x2 chroma path): geometry not covered";
             return SRCNN_B200_ECUDA;
         }
@@ -497,10 +499,12 @@ int run_group(srcnn_b200_ctx* ctx, Plan& p, unsigned G, const uint8_t* d_src, ui
     float* Yp = static_cast<float*>(ctx->yprime.p);
     cudaStream_t s = ctx->stream;
     Stamp st(ctx);                                                  /* timings then describe the whole group */
-    if (!launch_prep(d_src + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, 0, false,
-                     Y16, g, p.r0, vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(),
-                     vc->host.cleft.data(), hy->host.cleft.data(), hc->host.cleft.data(), s, CS, ps_csrc,
-                     G, ib, y16_f, csrc_f)) return 1;                /* geometry not covered: nothing launched */
+    const int lp = launch_prep(d_src + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, 0, false,
+                               Y16, g, p.r0, vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(),
+                               vc->host.cleft.data(), hy->host.cleft.data(), hc->host.cleft.data(), s, CS, ps_csrc,
+                               G, ib, y16_f, csrc_f);
+    if (lp < 0) return fail_cuda(ctx, cudaGetLastError(), "prep_kernel launch");
+    if (!lp) return 1;                                              /* geometry not covered: nothing launched */
     ctx->launches++;
     st.mark(); st.skip(3);
     if (launch_conv_tc(ctx->tc, Y16, g, p.ow, p.oh, Yp, p.r0, p.r1, ctx->num_sms, s, nullptr, G, yp_f)) {
@@ -510,7 +514,7 @@ int run_group(srcnn_b200_ctx* ctx, Plan& p, unsigned G, const uint8_t* d_src, ui
     ctx->launches++;
     st.mark();
     if (!launch_color_out_up(Yp, CS, ps_csrc, p.w, p.s0, vc->view, hc->view, p.ow, p.r0, p.r1, p.d, d_out, d_conv, s,
-                             G, yp_f, csrc_f, ob, cb)) {
+                             ctx->num_sms, G, yp_f, csrc_f, ob, cb)) {
         ctx->err = "frame group: colour-out geometry not covered"; return SRCNN_B200_ECUDA;
     }
     ctx->launches++;
@@ -695,9 +699,20 @@ int srcnn_b200_sync(srcnn_b200_ctx* ctx)
 }
 void* srcnn_b200_stream(srcnn_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
-int srcnn_b200_pass_host_rows(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
-                              float multiply, int filter, unsigned row0, unsigned row1,
-                              uint8_t* out_rows, uint8_t* conv_rows)
+/* An error in the middle of a host pipeline leaves kernels and asynchronous copies of earlier sub-strips in flight -- to the
+ * caller's buffers (which it is about to free) and to the context's staging slots (which the next call reuses).  Drain all
+ * three streams before the error is reported, and clear the sticky error state. */
+static void drain_streams(srcnn_b200_ctx* ctx)
+{
+    cudaStreamSynchronize(ctx->stream_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream_out);
+    cudaGetLastError();
+}
+
+static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                               float multiply, int filter, unsigned row0, unsigned row1,
+                               uint8_t* out_rows, uint8_t* conv_rows)
 {
     if (!ctx || !src || !out_rows) return SRCNN_B200_EINVAL;
     Plan p; int rc = make_plan(w, h, d, multiply, filter, row0, row1, p);
@@ -793,6 +808,15 @@ int srcnn_b200_pass_host_rows(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned 
     return 0;                                 /* (the plane getters describe the last sub-strip) */
 }
 
+int srcnn_b200_pass_host_rows(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                              float multiply, int filter, unsigned row0, unsigned row1,
+                              uint8_t* out_rows, uint8_t* conv_rows)
+{
+    const int rc = pass_host_rows_impl(ctx, src, w, h, d, multiply, filter, row0, row1, out_rows, conv_rows);
+    if (rc && ctx) drain_streams(ctx);
+    return rc;
+}
+
 int srcnn_b200_pass_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
                          float multiply, int filter, uint8_t* out, uint8_t* conv)
 {
@@ -804,8 +828,8 @@ int srcnn_b200_pass_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, un
     return srcnn_b200_pass_host_rows(ctx, src, w, h, d, multiply, filter, 0, oh, out, conv);
 }
 
-int srcnn_b200_process_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
-                            float multiply, int filter, int stepscale, uint8_t* out, uint8_t* conv)
+static int process_host_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                             float multiply, int filter, int stepscale, uint8_t* out, uint8_t* conv)
 {
     if (!ctx || !src || !w || !h || !d) return SRCNN_B200_EINVAL;
     if (d != 3 && d != 4) return SRCNN_B200_EINVAL;
@@ -853,6 +877,14 @@ int srcnn_b200_process_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w,
     return 0;
 }
 
+int srcnn_b200_process_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                            float multiply, int filter, int stepscale, uint8_t* out, uint8_t* conv)
+{
+    const int rc = process_host_impl(ctx, src, w, h, d, multiply, filter, stepscale, out, conv);
+    if (rc && rc != SRCNN_B200_ENOTHING && ctx) drain_streams(ctx);
+    return rc;
+}
+
 /* frames [f0, f0+G) of a batch, device-resident: the grouped route when it applies, run_pass per frame otherwise */
 static int batch_frames_device(srcnn_b200_ctx* ctx, unsigned w, unsigned h, unsigned d, float multiply, int filter, unsigned G,
                                const uint8_t* d_src, uint8_t* d_out, uint8_t* d_conv)
@@ -892,8 +924,8 @@ int srcnn_b200_batch_device(srcnn_b200_ctx* ctx, const void* d_frames, unsigned 
     return 0;
 }
 
-int srcnn_b200_batch_host(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n, unsigned w, unsigned h,
-                          unsigned d, float multiply, int filter, uint8_t* out, uint8_t* conv)
+static int batch_host_impl(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n, unsigned w, unsigned h,
+                           unsigned d, float multiply, int filter, uint8_t* out, uint8_t* conv)
 {
     if (!ctx || !frames || !out) return SRCNN_B200_EINVAL;
     if (n == 0) return 0;
@@ -932,6 +964,14 @@ int srcnn_b200_batch_host(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n
     CK(cudaStreamSynchronize(ctx->stream_out));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+int srcnn_b200_batch_host(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n, unsigned w, unsigned h,
+                          unsigned d, float multiply, int filter, uint8_t* out, uint8_t* conv)
+{
+    const int rc = batch_host_impl(ctx, frames, n, w, h, d, multiply, filter, out, conv);
+    if (rc && ctx) drain_streams(ctx);
+    return rc;
 }
 
 void* srcnn_b200_host_alloc(size_t bytes)

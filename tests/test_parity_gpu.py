@@ -113,6 +113,12 @@ CASES = [
     dict(id="thin-3x200", kind="uniform", h=3, w=200, d=3, m=2.0, f=S.BICUBIC, s=False),
     dict(id="downscale-x0.5", kind="smooth", h=64, w=96, d=3, m=0.5, f=S.BICUBIC, s=False),
     dict(id="bad-filter-id", kind="uniform", h=16, w=16, d=3, m=2.0, f=9, s=False),
+    # magnifications in (1, 1.5): the separate colour-in / resize / pack kernels (the fused front end starts at 1.5)
+    dict(id="x1.25-bicubic", kind="uniform", h=64, w=88, d=3, m=1.25, f=S.BICUBIC, s=False),
+    dict(id="x1.4-lanczos-rgba", kind="smooth", h=50, w=70, d=4, m=1.4, f=S.LANCZOS3, s=False),
+    dict(id="x1.1-bspline", kind="uniform", h=40, w=60, d=3, m=1.1, f=S.BSPLINE, s=False),
+    dict(id="x1.5-bicubic-rgba", kind="uniform", h=66, w=90, d=4, m=1.5, f=S.BICUBIC, s=False),
+    dict(id="x2-wide-lanczos", kind="uniform", h=40, w=700, d=3, m=2.0, f=S.LANCZOS3, s=False),
 ]
 
 
@@ -151,6 +157,48 @@ def test_interpolated_plane_and_network_output(ctx, filt):
     ctx.pass_host(img, 2.0, filt)
     _, gyp = ctx.get_plane(4, (120, 168))
     assert np.array_equal(gyp, yprime)
+
+
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+@pytest.mark.parametrize("d", [3, 4])
+def test_equal_size_pass(ctx, mode, d):
+    """multiply == 1 without step-scale: no axis is resampled.  DELIBERATE deviation from the reference, whose equal-size
+    shortcut copies only HALF of each plane (sizeof(unsigned short) instead of sizeof(float), src/frawscale.cpp:185-193)
+    and leaves the rest uninitialised heap.  Defined behaviour here: the whole plane is copied, i.e. the result is
+    colour-in -> conv I/II/III on the un-resized Y -> colour-out, composed below from the oracle's own stages.  The rows
+    the reference does compute from valid data (the top half minus the conv halo) must also equal the reference's own
+    ProcessSRCNN output."""
+    h, w = 46, 62
+    img = O.synth("uniform", h, w, d, 17)
+    o = O.best()
+    pl = o.color_in(img)
+    yprime = o.convs(pl[0])
+    want = o.color_out([yprime] + pl[1:])
+    want_conv = yprime.astype(np.uint8)
+    ctx.set_conv_mode(mode[1])
+    for call in ("pass", "process", "dropin"):
+        if call == "pass":
+            out, conv = ctx.pass_host(img, 1.0, S.BICUBIC, True)
+        elif call == "process":
+            rc, out, conv = ctx.process(img, 1.0, S.BICUBIC, False, True)
+            assert rc == 0
+        else:
+            if mode[0] == "exact":
+                continue                                   # the process-wide context of the C++ API runs tensor mode
+            rc, out, conv = S.process_srcnn(img, 1.0, S.BICUBIC, False, True)
+            assert rc == 0
+        _check_u8(call + " rgb", out, want, mode[0] == "exact")
+        _check_u8(call + " conv", conv, want_conv, mode[0] == "exact")
+    # chroma / alpha come out exactly (no arithmetic besides the colour conversion) in both modes
+    if d == 4:
+        assert np.array_equal(np.asarray(out).reshape(h, w, d)[..., 3], img[..., 3])
+    # the part of the reference's own output that is computed from initialised memory: rows < h/2 - 6
+    rc_r, out_r, _ = o.process(img, 1.0, S.BICUBIC, False, False)
+    assert rc_r == 0
+    valid = h // 2 - 6
+    _check_u8("reference top rows", np.asarray(out).reshape(h, w, d)[:valid], out_r.reshape(h, w, d)[:valid], mode[0] == "exact")
+    # step mode with an effective factor of 1 produces nothing (src/libsrcnn.cpp:1007-1008)
+    assert ctx.process(img, 1.0, S.BICUBIC, True, True)[0] == S.ENOTHING
 
 
 @pytest.mark.parametrize("d,hw,filt", [(3, (61, 83), S.BICUBIC), (4, (47, 130), S.LANCZOS3), (3, (200, 333), S.BSPLINE),
@@ -373,3 +421,67 @@ def test_full_size_properties(ctx, case):
     ih = coh - 16 if ch < case["h"] else coh
     iw = cow - 16 if cw < case["w"] else cow
     assert np.array_equal(ex[:ih, :iw], o_crop[:ih, :iw])
+
+
+def _oracle_rows(img, m, filt, step, r0, r1, margin_src=24):
+    """oracle output rows [r0, r1) of the full result, computed from just the source rows they depend on: the resampling
+    maps are shift-invariant for a crop that starts on a whole source row when m is an integer, so a crop with `margin_src`
+    extra source rows on each cut side (conv halo 6 output rows + the widest resampling window) reproduces the interior
+    bit for bit.  Returns (rgb rows, conv rows)."""
+    h = img.shape[0]
+    mi = int(m)
+    assert mi == m
+    a = max(0, r0 // mi - margin_src)
+    b = min(h, (r1 + mi - 1) // mi + margin_src)
+    rc, o, c = O.best().process(img[a:b], m, filt, step, True)
+    assert rc == 0
+    ow = img.shape[1] * mi
+    o = o.reshape((b - a) * mi, ow, img.shape[2]); c = c.reshape((b - a) * mi, ow)
+    return o[r0 - a * mi: r1 - a * mi], c[r0 - a * mi: r1 - a * mi]
+
+
+def test_c3_strips_directly_against_oracle(ctx):
+    """BASELINE config 3 (7680x4320 RGBA x2 -> 15360x8640, 8 row strips): both border strips and an interior strip of the
+    TENSOR path directly against the oracle run on the source rows those strips depend on."""
+    img = O.synth("uniform", 4320, 7680, 4, 43)
+    oh = 8640
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    for k in (0, 3, 7):
+        r0, r1 = S.strip_rows(oh, 8, k)
+        got, gconv = ctx.pass_host(img, 2.0, S.BICUBIC, True, rows=(r0, r1))
+        want, wconv = _oracle_rows(img, 2.0, S.BICUBIC, False, r0, r1)
+        _check_u8("strip %d rgba" % k, got, want, False)
+        _check_u8("strip %d conv" % k, gconv, wconv, False)
+        if k == 3:                                        # and bit for bit in exact mode, one strip
+            ctx.set_conv_mode(S.CONV_EXACT)
+            got, gconv = ctx.pass_host(img, 2.0, S.BICUBIC, True, rows=(r0, r1))
+            ctx.set_conv_mode(S.CONV_TENSOR)
+            _check_u8("strip %d rgba exact" % k, got, want, True)
+            _check_u8("strip %d conv exact" % k, gconv, wconv, True)
+
+
+def test_c4_frames_directly_against_oracle(ctx):
+    """BASELINE config 4 (512x512 RGB x2 Lanczos-3 frames, batched): every frame of a batch that spans two frame groups,
+    TENSOR path, directly against the oracle"""
+    n = 18
+    frames = np.stack([O.synth("uniform", 512, 512, 3, 44 + i) for i in range(n)])
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    out, conv = ctx.batch(frames, 2.0, S.LANCZOS3, want_conv=True)
+    for i in (0, 1, 7, 15, 16, 17):
+        rc, want, wconv = O.best().process(frames[i], 2.0, S.LANCZOS3, False, True)
+        assert rc == 0
+        _check_u8("frame %d rgb" % i, out[i], want.reshape(1024, 1024, 3), False)
+        _check_u8("frame %d conv" % i, conv[i], wconv.reshape(1024, 1024), False)
+
+
+def test_c5_full_size_directly_against_oracle(ctx):
+    """BASELINE config 5 at full size (3840x2160 RGB x1.5 B-spline, step-scale ON, convolution output ON): the whole
+    frame, TENSOR path through the ProcessSRCNN-level entry point, directly against the oracle"""
+    img = O.synth("uniform", 2160, 3840, 3, 45)
+    rc_o, want, wconv = O.best().process(img, 1.5, S.BSPLINE, True, True)
+    assert rc_o == 0
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    rc, out, conv = ctx.process(img, 1.5, S.BSPLINE, True, True)
+    assert rc == 0 and out.shape == (3240, 5760, 3)
+    _check_u8("c5 rgb", out, want.reshape(3240, 5760, 3), False)
+    _check_u8("c5 conv", conv, wconv.reshape(3240, 5760), False)
