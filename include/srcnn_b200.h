@@ -41,7 +41,8 @@ typedef struct srcnn_b200_ctx srcnn_b200_ctx;
 
 int         srcnn_b200_abi_version(void);
 int         srcnn_b200_device_count(void);
-/* one context = one GPU + one stream + grow-only device/pinned buffers.  Not thread-safe; use one per thread. */
+/* one context = one GPU + one stream + grow-only device/pinned buffers.  Not thread-safe; use one per thread.
+ * Limits: output and source heights <= 65535 rows per pass (rows map to gridDim.y); larger images: row strips. */
 int         srcnn_b200_create(int device, srcnn_b200_ctx** out);
 void        srcnn_b200_destroy(srcnn_b200_ctx* ctx);
 const char* srcnn_b200_last_error(const srcnn_b200_ctx* ctx);
@@ -52,6 +53,12 @@ int         srcnn_b200_get_conv_mode(const srcnn_b200_ctx* ctx);
  * including the step-scale chain (src/libsrcnn.cpp:980-1061); returns the number of passes (0 = nothing produced). */
 void        srcnn_b200_output_dims(unsigned w, unsigned h, float multiply, unsigned* ow, unsigned* oh);
 int         srcnn_b200_process_dims(unsigned w, unsigned h, float multiply, int stepscale, unsigned* ow, unsigned* oh);
+/* 1 if the whole call produces a convolution plane.  Always 1 without step-scale; in the step-scale chain only the pass with
+ * cnt + 1 == repeat receives the caller's convbuff (src/libsrcnn.cpp:1024-1028), and the loop breaks before it when the
+ * remaining factor is exactly 1 (x8 = x2 x2 x2 then x1): the reference then leaves *convbuff / *convbuffsz untouched. */
+int         srcnn_b200_process_has_conv(unsigned w, float multiply, int stepscale);
+/* the factors of the step-scale passes that actually run (src/libsrcnn.cpp:997-1008); returns their number */
+int         srcnn_b200_step_factors(unsigned w, float multiply, float* factors, int maxn);
 
 /* ---- one pass = reference libsrcnn::doSRCNN (src/libsrcnn.cpp:628-923) --------------------------------------
  * colour-in -> resize (Y: `filter`; Cb/Cr/A: bilinear, or box for nearest) -> conv I/II/III fused -> colour-out.
@@ -67,6 +74,15 @@ int srcnn_b200_pass_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, un
 int srcnn_b200_pass_host_rows(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
                               float multiply, int filter, unsigned row0, unsigned row1,
                               uint8_t* out_rows, uint8_t* conv_rows);
+
+/* Stream-ordered, NON-BLOCKING variant of srcnn_b200_pass_host: uploads, kernels and downloads are only
+ * enqueued.  src / out / conv must stay valid until srcnn_b200_wait returns and should be pinned (srcnn_b200_host_alloc);
+ * with pageable buffers the copies make the call wait.  Up to two calls are in flight per context: the upload of call k+1
+ * overlaps the kernels and the download of call k.  srcnn_b200_wait blocks until every asynchronous pass of the context has
+ * landed and returns the first CUDA error, if any.  Any blocking entry point of the same context waits first, too. */
+int srcnn_b200_pass_host_async(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                               float multiply, int filter, uint8_t* out, uint8_t* conv);
+int srcnn_b200_wait(srcnn_b200_ctx* ctx);
 
 /* Host-side geometry of a strip (no GPU needed): the rows [*halo_row0,*halo_row1) of the interpolated planes the strip
  * computes (strip +- 6 clipped to the image) and the source rows [*src_row0,*src_row1) it reads / uploads. */
@@ -85,7 +101,8 @@ void* srcnn_b200_stream(srcnn_b200_ctx* ctx);            /* cudaStream_t */
 
 /* ---- whole call = reference ProcessSRCNN (src/libsrcnn.cpp:943-1064) -----------------------------------------
  * incl. the step-scale chain; 8-bit intermediates of the chain stay in HBM (quantisation preserved).
- * out must hold the srcnn_b200_process_dims size * d; conv (or NULL) ow*oh of the LAST pass. */
+ * out must hold the srcnn_b200_process_dims size * d; conv (or NULL) ow*oh of the LAST pass -- written only when
+ * srcnn_b200_process_has_conv says the reference would produce it. */
 int srcnn_b200_process_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
                             float multiply, int filter, int stepscale, uint8_t* out, uint8_t* conv);
 
@@ -100,6 +117,26 @@ int srcnn_b200_batch_host(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n
 int srcnn_b200_batch_device(srcnn_b200_ctx* ctx, const void* d_frames, unsigned n, unsigned w, unsigned h,
                             unsigned d, float multiply, int filter, void* d_out, void* d_conv);
 
+/* ---- one host call, ALL GPUs of the box (single process; reference: the OpenMP teams inside ProcessSRCNN,
+ * src/libsrcnn.cpp:791, 817, 495, spread one call over every host core) ------------------------------------------
+ * srcnn_b200_multi owns one context + one worker thread per device.  A pass over one image is cut into row strips
+ * [oh*g/G, oh*(g+1)/G), one per GPU, each recomputing its 6-row halo (no exchange, results bit-identical to the
+ * single-GPU call); a batch is cut into contiguous blocks of frames.  devices == NULL / ndev <= 0: every visible device.
+ * Calls on one handle are serialised.  Images with fewer than SRCNN_B200_MULTI_MIN_ROWS (256) output rows per GPU use
+ * fewer GPUs.  Step-scale chains run every pass on all GPUs, with the 8-bit intermediates in pinned host memory. */
+typedef struct srcnn_b200_multi srcnn_b200_multi;
+int         srcnn_b200_multi_create(const int* devices, int ndev, srcnn_b200_multi** out);
+void        srcnn_b200_multi_destroy(srcnn_b200_multi* m);
+int         srcnn_b200_multi_device_count(const srcnn_b200_multi* m);
+const char* srcnn_b200_multi_last_error(const srcnn_b200_multi* m);
+int         srcnn_b200_multi_set_conv_mode(srcnn_b200_multi* m, int mode);
+int srcnn_b200_multi_pass_host(srcnn_b200_multi* m, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                               float multiply, int filter, uint8_t* out, uint8_t* conv);
+int srcnn_b200_multi_process_host(srcnn_b200_multi* m, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                                  float multiply, int filter, int stepscale, uint8_t* out, uint8_t* conv);
+int srcnn_b200_multi_batch_host(srcnn_b200_multi* m, const uint8_t* frames, unsigned n, unsigned w, unsigned h,
+                                unsigned d, float multiply, int filter, uint8_t* out, uint8_t* conv);
+
 /* pinned host memory for fast DMA (cudaHostAlloc / cudaFreeHost) */
 void* srcnn_b200_host_alloc(size_t bytes);
 void  srcnn_b200_host_free(void* p);
@@ -110,12 +147,18 @@ void  srcnn_b200_host_free(void* p);
 int srcnn_b200_get_plane(srcnn_b200_ctx* ctx, int which, float* host, size_t cap,
                          unsigned* row0, unsigned* rows, unsigned* width);
 /* The tensor-core path consumes the interpolated Y plane as FP16 and never writes its FP32 form to HBM.  Switch this
- * on (before the pass) to have plane 0 written as well, for srcnn_b200_get_plane(ctx, 0, ...).  Default off. */
+ * on (before the pass) to have plane 0 written as well, for srcnn_b200_get_plane(ctx, 0, ...).  Default off.
+ *   on = 1: the FP32 Y plane AND the output-size Cb / Cr / A planes, computed exactly like the reference (two roundings per
+ *           tap) -- the planes of the bit-exact route;
+ *   on = 2: the FP32 Y plane only, written by the PRODUCT route's own front-end kernel (x2: one double FMA per tap) -- what
+ *           the 1e-5 gate on the interpolated plane is checked on. */
 int srcnn_b200_set_keep_planes(srcnn_b200_ctx* ctx, int on);
 /* GPU time (ms, CUDA events on the context's stream) of the LAST pass's kernels:
  * [0] colour-in [1] resize pass 1 [2] resize pass 2 [3] conv-input pack [4] fused conv [5] colour-out [6] total.
  * Only recorded while srcnn_b200_set_timing(ctx, 1). */
 int srcnn_b200_set_timing(srcnn_b200_ctx* ctx, int on);
+/* host threads (1..64) that move result rows from the pinned staging slots into a pageable destination buffer */
+int srcnn_b200_set_copy_threads(srcnn_b200_ctx* ctx, unsigned n);
 int srcnn_b200_last_timings(srcnn_b200_ctx* ctx, float* ms7);
 /* kernels launched by this context since creation */
 unsigned long long srcnn_b200_launch_count(const srcnn_b200_ctx* ctx);

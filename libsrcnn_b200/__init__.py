@@ -50,10 +50,23 @@ def lib():
         L.srcnn_b200_get_conv_mode.argtypes = [vp]
         L.srcnn_b200_output_dims.argtypes = [u, u, f, C.POINTER(u), C.POINTER(u)]; L.srcnn_b200_output_dims.restype = None
         L.srcnn_b200_process_dims.argtypes = [u, u, f, i, C.POINTER(u), C.POINTER(u)]
+        L.srcnn_b200_process_has_conv.argtypes = [u, f, i]
         L.srcnn_b200_strip_geometry.argtypes = [u, u, u, f, i, u, u] + [C.POINTER(u)] * 4
         L.srcnn_b200_pass_host.argtypes = [vp, vp, u, u, u, f, i, vp, vp]
         L.srcnn_b200_pass_host_rows.argtypes = [vp, vp, u, u, u, f, i, u, u, vp, vp]
         L.srcnn_b200_pass_device.argtypes = [vp, vp, u, u, u, f, i, u, u, vp, vp]
+        L.srcnn_b200_pass_host_async.argtypes = [vp, vp, u, u, u, f, i, vp, vp]
+        L.srcnn_b200_wait.argtypes = [vp]
+        L.srcnn_b200_set_copy_threads.argtypes = [vp, u]
+        L.srcnn_b200_step_factors.argtypes = [u, f, _f32p, i]
+        L.srcnn_b200_multi_create.argtypes = [_i32p, i, C.POINTER(vp)]
+        L.srcnn_b200_multi_destroy.argtypes = [vp]; L.srcnn_b200_multi_destroy.restype = None
+        L.srcnn_b200_multi_device_count.argtypes = [vp]
+        L.srcnn_b200_multi_last_error.argtypes = [vp]; L.srcnn_b200_multi_last_error.restype = C.c_char_p
+        L.srcnn_b200_multi_set_conv_mode.argtypes = [vp, i]
+        L.srcnn_b200_multi_pass_host.argtypes = [vp, vp, u, u, u, f, i, vp, vp]
+        L.srcnn_b200_multi_process_host.argtypes = [vp, vp, u, u, u, f, i, i, vp, vp]
+        L.srcnn_b200_multi_batch_host.argtypes = [vp, vp, u, u, u, u, f, i, vp, vp]
         L.srcnn_b200_sync.argtypes = [vp]
         L.srcnn_b200_stream.argtypes = [vp]; L.srcnn_b200_stream.restype = vp
         L.srcnn_b200_process_host.argtypes = [vp, vp, u, u, u, f, i, i, vp, vp]
@@ -209,6 +222,16 @@ class Context:
         self._ck(rc, "pass_host_rows")
         return out, (conv if want_conv else None)
 
+    def pass_host_async(self, img, multiply, filt, out, conv=None):
+        """non-blocking pass: img / out / conv should be pinned (pinned_empty) and must stay alive until wait()"""
+        h, w, d = img.shape
+        assert img.flags["C_CONTIGUOUS"] and img.dtype == np.uint8
+        self._ck(self.L.srcnn_b200_pass_host_async(self.h, _vp(img), w, h, d, multiply, int(filt), _vp(out), _vp(conv)),
+                 "pass_host_async")
+
+    def wait(self):
+        self._ck(self.L.srcnn_b200_wait(self.h), "wait")
+
     def pass_device(self, d_src, w, h, d, multiply, filt, d_out, d_conv=0, rows=None):
         """device pointers (ints); asynchronous on the context's stream"""
         ow, oh = output_dims(w, h, multiply)
@@ -231,6 +254,7 @@ class Context:
         if n == 0:
             return ENOTHING, None, None
         out = np.empty((oh, ow, d), np.uint8)
+        want_conv = want_conv and bool(self.L.srcnn_b200_process_has_conv(w, multiply, int(bool(stepscale))))
         conv = np.empty((oh, ow), np.uint8) if want_conv else None
         rc = self.L.srcnn_b200_process_host(self.h, _vp(img), w, h, d, multiply, int(filt), int(bool(stepscale)),
                                             _vp(out), _vp(conv))
@@ -318,6 +342,85 @@ class Context:
         cv = np.empty((h, w), np.uint8) if want_conv else None
         self._ck(self.L.srcnn_b200_stage_color_out(self.h, arr, w, h, d, _vp(o), _vp(cv)), "stage_color_out")
         return (o, cv) if want_conv else o
+
+
+class Multi:
+    """one host call over several GPUs of the box, single process (include/srcnn_b200.h: srcnn_b200_multi)"""
+
+    def __init__(self, devices=None, conv_mode=CONV_TENSOR):
+        self.L = lib()
+        h = C.c_void_p()
+        if devices is None:
+            rc = self.L.srcnn_b200_multi_create(None, 0, C.byref(h))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.L.srcnn_b200_multi_create(arr, len(devices), C.byref(h))
+        if rc != 0:
+            raise SrcnnError(rc, "srcnn_b200_multi_create(%r): no usable B200 (there is no CPU fallback)" % (devices,))
+        self.h = h
+        self._ck(self.L.srcnn_b200_multi_set_conv_mode(self.h, conv_mode), "set_conv_mode")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.srcnn_b200_multi_destroy(self.h); self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise SrcnnError(rc, "%s: %s" % (what, (self.L.srcnn_b200_multi_last_error(self.h) or b"").decode()))
+
+    @property
+    def ndev(self):
+        return int(self.L.srcnn_b200_multi_device_count(self.h))
+
+    def set_conv_mode(self, mode):
+        self._ck(self.L.srcnn_b200_multi_set_conv_mode(self.h, mode), "set_conv_mode")
+
+    def pass_host(self, img, multiply, filt=BICUBIC, want_conv=True, out=None, conv=None):
+        h, w, d = img.shape
+        img = np.ascontiguousarray(img, np.uint8)
+        ow, oh = output_dims(w, h, multiply)
+        if out is None:
+            out = np.empty((oh, ow, d), np.uint8)
+        if conv is None and want_conv:
+            conv = np.empty((oh, ow), np.uint8)
+        self._ck(self.L.srcnn_b200_multi_pass_host(self.h, _vp(img), w, h, d, multiply, int(filt), _vp(out),
+                                                   _vp(conv) if want_conv else None), "multi_pass_host")
+        return out, (conv if want_conv else None)
+
+    def process(self, img, multiply, filt=BICUBIC, stepscale=False, want_conv=True):
+        h, w, d = img.shape
+        img = np.ascontiguousarray(img, np.uint8)
+        n, ow, oh = process_dims(w, h, multiply, stepscale)
+        if n == 0:
+            return ENOTHING, None, None
+        out = np.empty((oh, ow, d), np.uint8)
+        want_conv = want_conv and bool(self.L.srcnn_b200_process_has_conv(w, multiply, int(bool(stepscale))))
+        conv = np.empty((oh, ow), np.uint8) if want_conv else None
+        rc = self.L.srcnn_b200_multi_process_host(self.h, _vp(img), w, h, d, multiply, int(filt), int(bool(stepscale)),
+                                                  _vp(out), _vp(conv))
+        if rc != 0:
+            return rc, None, None
+        return rc, out, conv
+
+    def batch(self, frames, multiply, filt=BICUBIC, want_conv=False, out=None, conv=None):
+        n, h, w, d = frames.shape
+        frames = np.ascontiguousarray(frames, np.uint8)
+        ow, oh = output_dims(w, h, multiply)
+        if out is None:
+            out = np.empty((n, oh, ow, d), np.uint8)
+        if not want_conv:
+            conv = None
+        elif conv is None:
+            conv = np.empty((n, oh, ow), np.uint8)
+        self._ck(self.L.srcnn_b200_multi_batch_host(self.h, _vp(frames), n, w, h, d, multiply, int(filt), _vp(out), _vp(conv)),
+                 "multi_batch_host")
+        return out, conv
+
+
+def device_count():
+    return int(lib().srcnn_b200_device_count())
 
 
 def pinned_empty(shape, dtype=np.uint8):

@@ -161,6 +161,8 @@ constexpr int kUpMaxCols = 32 * kUpIters;     /* source columns a warp may need:
 constexpr int kUpRowsMax = 16;                /* consecutive output rows per CTA (the horizontal table entries stay in registers);
                                                  fewer for small images so that the grid still fills the SMs */
 
+__device__ __forceinline__ int up_pos(int j) { return (j >> 1) + (j & 1) * (kUpMaxCols / 2); }
+
 /* pack2 entry of a two-tap table (built on the host, srcnn_ctx.cu): x = left + (index of tap A), y = wA bits, z = wB bits,
  * w = left + (index of tap B); B is the tap whose weight is 0 or a power of two */
 template <int D, bool CONV>
@@ -176,9 +178,10 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
         out += (size_t)blockIdx.z * out_fstride;
         if (CONV) conv += (size_t)blockIdx.z * conv_fstride;
     }
-    /* the intermediate (vertically resampled) plane: every WARP stages the source columns of its own 128 pixels (so rows
-     * need only __syncwarp, warps run independently), double-buffered by row parity */
-    __shared__ float tS[8][2][NC][kUpMaxCols];
+    /* the intermediate (vertically resampled) plane: every WARP stages the source columns of its own 128 pixels, so rows need
+     * only __syncwarp and warps run independently.  One buffer per warp (two warp barriers per row): the shared-memory
+     * addresses of a lane are then loop-invariant registers -- this kernel is bound by instruction issue, not by HBM */
+    __shared__ float tS[8][NC][kUpMaxCols];
     const unsigned wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned xw = blockIdx.x * kUpBlockPx + wq * kUpWarpPx;     /* first pixel of this warp */
     if (xw >= ow) return;                                             /* (whole warps only: no block barrier below) */
@@ -187,13 +190,22 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
     const int c_lo = min(hb.x, hb.w), ncols = max(he.x, he.w) - c_lo + 1;   /* source columns [c_lo, c_lo + ncols) */
     const unsigned x0 = xw + lane * 4;
     const bool active = x0 < ow;
-    int ia[4], ib[4]; float hA[4], hB[4];
+    float (*t)[kUpMaxCols] = tS[wq];
+    const float* ta[4]; const float* tb[4]; float hA[4], hB[4];
     #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int4 hp = active ? __ldg(hpack + x0 + i) : make_int4(c_lo, 0, 0, c_lo);
-        ia[i] = hp.x - c_lo; ib[i] = hp.w - c_lo; hA[i] = __int_as_float(hp.y); hB[i] = __int_as_float(hp.z);
+        /* shared-memory position of staged column j: even columns in the first half of the row, odd ones in the second.  The
+         * four pixels of a lane sit two source columns after its neighbour's, so a warp reads stride-2 columns: with the
+         * natural order that is a 2-way bank conflict on every load (ncu, round 1: 42 % of this kernel's shared wavefronts) */
+        ta[i] = &t[0][up_pos(hp.x - c_lo)]; tb[i] = &t[0][up_pos(hp.w - c_lo)];
+        hA[i] = __int_as_float(hp.y); hB[i] = __int_as_float(hp.z);
     }
+    /* where this lane stages its columns lane, lane + 32, lane + 64: up_pos(lane + 32 it) == up_pos(lane) + 16 it */
+    float* const ts0 = &t[0][up_pos((int)lane)];
     const unsigned ry0 = blockIdx.y * rpc, ry1 = min(ry0 + rpc, nrows);
+    /* 32-bit element offsets (checked on the host): one 64-bit multiply-add per source row instead of one per load */
+    const unsigned cs = (unsigned)cstride, col0 = (unsigned)c_lo + lane;
     /* software pipeline over the rows: the source samples (and Y') of row r+1 are requested before row r is computed, so
      * their latency hides behind the colour arithmetic */
     float pa[kUpIters][NC], pb[kUpIters][NC], pvA = 0.f, pvB = 0.f;
@@ -201,61 +213,57 @@ color_out_up_kernel(const float* __restrict__ yp, const float* __restrict__ csrc
     auto prefetch = [&](unsigned ry) {
         const int4 vp = __ldg(vpack + row0 + ry);                     /* vertical taps of image row row0 + ry */
         pvA = __int_as_float(vp.y); pvB = __int_as_float(vp.z);
-        const float* rA = csrc + (size_t)(vp.x - (int)src_row0) * w + c_lo;
-        const float* rB = csrc + (size_t)(vp.w - (int)src_row0) * w + c_lo;
+        const float* rA = csrc + ((unsigned)(vp.x - (int)src_row0) * w + col0);
+        const float* rB = csrc + ((unsigned)(vp.w - (int)src_row0) * w + col0);
         #pragma unroll
-        for (int it = 0; it < kUpIters; it++) {
-            const int j = (int)lane + 32 * it;
-            if (j < ncols) {
-                #pragma unroll
-                for (int k = 0; k < NC; k++) { pa[it][k] = __ldg(rA + k * cstride + j); pb[it][k] = __ldg(rB + k * cstride + j); }
-            }
+        for (int k = 0; k < NC; k++) {
+            const float* qa = rA + k * cs; const float* qb = rB + k * cs;
+            #pragma unroll
+            for (int it = 0; it < kUpIters; it++)
+                if ((int)lane + 32 * it < ncols) { pa[it][k] = __ldg(qa + 32 * it); pb[it][k] = __ldg(qb + 32 * it); }
         }
-        if (active) py = __ldg(reinterpret_cast<const float4*>(yp + (size_t)ry * ow + x0));
+        if (active) py = __ldg(reinterpret_cast<const float4*>(yp + ((size_t)ry * ow + x0)));
     };
     /* up to here only constant tables were read: as a programmatic dependent launch this much overlaps the conv kernel's
      * tail; Y' (and, two kernels back, the chroma samples) is read from here on */
     pdl_wait();
     if (ry0 < ry1) prefetch(ry0);
-    for (unsigned ry = ry0; ry < ry1; ry++) {
-        float (*t)[kUpMaxCols] = tS[wq][ry & 1];
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(out) + ((size_t)ry0 * ow + x0) / 4 * D;
+    uint32_t* c32 = CONV ? reinterpret_cast<uint32_t*>(conv) + ((size_t)ry0 * ow + x0) / 4 : nullptr;
+    const unsigned ostep = ow / 4 * D, cstep = ow / 4;
+    for (unsigned ry = ry0; ry < ry1; ry++, o32 += ostep, c32 += cstep) {
         #pragma unroll
         for (int it = 0; it < kUpIters; it++) {
-            const int j = (int)lane + 32 * it;
-            if (j < ncols) {
+            if ((int)lane + 32 * it < ncols) {
                 #pragma unroll
-                for (int k = 0; k < NC; k++) t[k][j] = mix2f(pvA, pa[it][k], pvB, pb[it][k]);
+                for (int k = 0; k < NC; k++) ts0[16 * it + k * kUpMaxCols] = mix2f(pvA, pa[it][k], pvB, pb[it][k]);
             }
         }
         const float4 y4 = py;
-        __syncwarp();                   /* (the other parity's buffer was last read before the previous row's __syncwarp) */
+        __syncwarp();
         if (ry + 1 < ry1) prefetch(ry + 1);
-        if (!active) continue;              /* (a lane without pixels still staged its columns above) */
-        const size_t i0 = (size_t)ry * ow + x0;
-        const float Y[4] = { y4.x, y4.y, y4.z, y4.w };
-        uint32_t bytes[4 * D];
-        #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float c[NC];
+        if (active) {                       /* (a lane without pixels still staged its columns above) */
+            const float Y[4] = { y4.x, y4.y, y4.z, y4.w };
+            uint32_t bytes[4 * D];
             #pragma unroll
-            for (int k = 0; k < NC; k++) c[k] = mix2f(hA[i], t[k][ia[i]], hB[i], t[k][ib[i]]);
-            rgb_of(Y[i], c[0], c[1], bytes[i * D], bytes[i * D + 1], bytes[i * D + 2]);
-            if (D == 4) bytes[i * D + 3] = to_u8(c[NC - 1]);
+            for (int i = 0; i < 4; i++) {
+                float c[NC];
+                #pragma unroll
+                for (int k = 0; k < NC; k++) c[k] = mix2f(hA[i], ta[i][k * kUpMaxCols], hB[i], tb[i][k * kUpMaxCols]);
+                rgb_of(Y[i], c[0], c[1], bytes[i * D], bytes[i * D + 1], bytes[i * D + 2]);
+                if (D == 4) bytes[i * D + 3] = to_u8(c[NC - 1]);
+            }
+            uint32_t wds[D];
+            #pragma unroll
+            for (int wi = 0; wi < D; wi++) wds[wi] = pack4(bytes[wi * 4], bytes[wi * 4 + 1], bytes[wi * 4 + 2], bytes[wi * 4 + 3]);
+            if (D == 4) {
+                *reinterpret_cast<uint4*>(o32) = make_uint4(wds[0], wds[1], wds[2], wds[D - 1]);
+            } else {
+                o32[0] = wds[0]; o32[1] = wds[1]; o32[2] = wds[2];
+            }
+            if (CONV) *c32 = pack4(__float2uint_rz(Y[0]), __float2uint_rz(Y[1]), __float2uint_rz(Y[2]), __float2uint_rz(Y[3]));
         }
-        uint32_t wds[D];
-        #pragma unroll
-        for (int wi = 0; wi < D; wi++)
-            wds[wi] = bytes[wi * 4] | (bytes[wi * 4 + 1] << 8) | (bytes[wi * 4 + 2] << 16) | (bytes[wi * 4 + 3] << 24);
-        const size_t qi = i0 / 4;
-        if (D == 4) {
-            reinterpret_cast<uint4*>(out)[qi] = make_uint4(wds[0], wds[1], wds[2], wds[D - 1]);
-        } else {
-            uint32_t* p = reinterpret_cast<uint32_t*>(out) + qi * 3;
-            p[0] = wds[0]; p[1] = wds[1]; p[2] = wds[2];
-        }
-        if (CONV)
-            reinterpret_cast<uint32_t*>(conv)[qi] = __float2uint_rz(Y[0]) | (__float2uint_rz(Y[1]) << 8) |
-                                                    (__float2uint_rz(Y[2]) << 16) | (__float2uint_rz(Y[3]) << 24);
+        __syncwarp();                       /* every lane has read this row's columns before the next row overwrites them */
     }
 }
 
@@ -286,6 +294,7 @@ bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, uns
     if (nframes == 0) nframes = 1;
     if (nframes > 1 && ((yp_fstride % 4) || (out_fstride % 16) || (conv && (conv_fstride % 4)))) return false;
     if (!vc.pack2 || !hc.pack2 || (ow % 4) || row1 <= row0) return false;
+    if (cstride * (size_t)(d - 1) >= ((size_t)1 << 30)) return false;       /* 32-bit element offsets into the chroma planes */
     if (!al(yp, 16) || !al(out, d == 4 ? 16 : 4) || (conv && !al(conv, 4))) return false;
     const unsigned gx = (ow + kUpBlockPx - 1) / kUpBlockPx * nframes, nrows = row1 - row0;   /* (x nframes: for the wave estimate) */
     /* rows per CTA: 4 CTAs of 64-72 registers x 256 threads are resident per SM; pick the row count that minimises

@@ -19,13 +19,21 @@ __device__ __forceinline__ uint32_t to_u8(float f)
 
 __device__ __forceinline__ void rgb_of(float y, float cb, float cr, uint32_t& r, uint32_t& g, uint32_t& b)
 {
-    /* x / 32.f and x / 64.f are written as multiplications by the exact reciprocal: bit-identical to the IEEE division
-     * whenever the quotient is a normal number, and it always is here (cb - 128 and cr - 128 are 0 or >= 2^-17 in
-     * magnitude, so a non-zero numerator is >= 2^-17) */
+    /* The reference computes 45.f * fCr / 32.f, (11.f * fCb + 23.f * fCr) / 32.f and 113.f * fCb / 64.f.  Dividing by a power
+     * of two is exact and commutes with every rounding as long as nothing underflows: fl(45 c) / 32 == fl((45/32) c) and
+     * fl(fl(11 c) + fl(23 d)) / 32 == fl(fl((11/32) c) + fl((23/32) d)), with 45/32, 11/32, 23/32 and 113/64 exact in
+     * FP32.  Nothing underflows: cb - 128 and cr - 128 are 0 or >= 2^-17 in magnitude.  So each division folds into its
+     * multiplication, bit for bit (tests: test_stage_color_out_bit_exact and every exact-mode image test). */
     const float fcb = __fsub_rn(cb, 128.f), fcr = __fsub_rn(cr, 128.f);
-    r = to_u8(__fadd_rn(y, __fmul_rn(__fmul_rn(45.f, fcr), 0.03125f)));
-    g = to_u8(__fsub_rn(y, __fmul_rn(__fadd_rn(__fmul_rn(11.f, fcb), __fmul_rn(23.f, fcr)), 0.03125f)));
-    b = to_u8(__fadd_rn(y, __fmul_rn(__fmul_rn(113.f, fcb), 0.015625f)));
+    r = to_u8(__fadd_rn(y, __fmul_rn(1.40625f, fcr)));
+    g = to_u8(__fsub_rn(y, __fadd_rn(__fmul_rn(0.34375f, fcb), __fmul_rn(0.71875f, fcr))));
+    b = to_u8(__fadd_rn(y, __fmul_rn(1.765625f, fcb)));
+}
+
+/* four byte values (each 0..255 in its own register) -> one little-endian word, three byte permutes */
+__device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3)
+{
+    return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
 }
 
 } // namespace srcnn

@@ -386,6 +386,272 @@ prep_kernel(const PrepParams p)
     }
 }
 
+/* ====================================================================================================================
+ * Front end of the PRODUCT route (x2-type magnification: chroma / alpha handed over at source resolution), second
+ * generation.  Same data flow and the same arithmetic as prep_kernel above, restructured around instruction count -- the
+ * kernel is issue-bound, not HBM-bound (profiles/r1_ncu_summary.md: 21 M warp instructions for 40 MB):
+ *   - every stage works on PAIRS of adjacent columns: 16-byte shared-memory accesses, half the address arithmetic, one
+ *     32-bit store of two FP16 conv-input samples;
+ *   - stages are mapped on the flattened (row, column-pair) index space, so nearly every lane has work (the first generation
+ *     walks 96-column chunks over a 68-column footprint);
+ *   - source pixels are fetched as 16-bit / 64-bit words instead of single bytes;
+ *   - the footprint and the table slices are found with warp reductions, no shared-memory atomics.
+ * FMA = true (tensor-core conv mode): one double fused multiply-add per tap.  The reference rounds the product and the sum
+ * separately (src/frawscale.cpp:313-328, 367-381); the fused form differs by < 2^-52 relative BEFORE the rounding to FP32,
+ * i.e. the FP32 plane is identical except where the double sum falls within ~1e-16 of an FP32 rounding boundary.  The
+ * north-star gate for this plane is 1e-5 relative; tests/test_parity_gpu.py checks it on this kernel's own FP32 output.
+ * FMA = false (bit-exact conv mode, plane getters): multiply and add rounded separately, bit-identical to the reference.
+ * Chroma / alpha never differ: their colour conversion is the reference's unfused FP32 expression in both modes.
+ * ==================================================================================================================== */
+/* byte k of `v` as a float without the slow I2F unit: 0x4B0000bb is 2^23 + bb, and the subtraction is exact */
+template <int K>
+__device__ __forceinline__ float byte_f32(uint32_t v)
+{
+    return __fsub_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440u | K)), 8388608.f);
+}
+
+/* two adjacent pixels: the raw words (requested early) and their channels as floats */
+template <int D>
+__device__ __forceinline__ void load_raw2(const uint8_t* __restrict__ p, uint32_t (&r)[3])
+{
+    if (D == 4) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));            /* 8-byte aligned: (row * w + col) even */
+        r[0] = v.x; r[1] = v.y; r[2] = 0;
+    } else {
+        const unsigned short* q = reinterpret_cast<const unsigned short*>(p); /* 2-byte aligned: 3 * (row * w + col), even */
+        r[0] = __ldg(q); r[1] = __ldg(q + 1); r[2] = __ldg(q + 2);
+    }
+}
+template <int D>
+__device__ __forceinline__ void unpack_px2(const uint32_t (&r)[3], float (&c)[2][D])
+{
+    if (D == 4) {
+        c[0][0] = byte_f32<0>(r[0]); c[0][1] = byte_f32<1>(r[0]); c[0][2] = byte_f32<2>(r[0]); c[0][D - 1] = byte_f32<3>(r[0]);
+        c[1][0] = byte_f32<0>(r[1]); c[1][1] = byte_f32<1>(r[1]); c[1][2] = byte_f32<2>(r[1]); c[1][D - 1] = byte_f32<3>(r[1]);
+    } else {
+        c[0][0] = byte_f32<0>(r[0]); c[0][1] = byte_f32<1>(r[0]); c[0][2] = byte_f32<0>(r[1]);
+        c[1][0] = byte_f32<1>(r[1]); c[1][1] = byte_f32<0>(r[2]); c[1][2] = byte_f32<1>(r[2]);
+    }
+}
+/* (double)f for a finite, non-negative, normal-or-zero float -- every Y sample is one -- with integer instructions instead of
+ * the conversion unit: sign 0, exponent re-biased by 1023 - 127 = 896, mantissa shifted into place */
+__device__ __forceinline__ double widen(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return __hiloint2double((int)(b ? (b >> 3) + 0x38000000u : 0u), (int)(b << 29));
+}
+
+template <int D, int WY, int SC, bool FMA>
+__global__ void __launch_bounds__(NT, 4)
+prep2_kernel(const PrepParams p)
+{
+    pdl_launch_dependents();                          /* the conv kernel may set itself up while this grid drains */
+    const uint8_t* const f_src = p.src + (size_t)blockIdx.z * p.src_fstride;
+    __half* const f_y16 = p.y16 ? p.y16 + (size_t)blockIdx.z * p.y16_fstride : nullptr;
+    float* const f_csrc = p.csrc + (size_t)blockIdx.z * p.csrc_fstride;
+    constexpr int NC = D - 1;
+    constexpr int NCP = SC / 2;                       /* column pairs per shared-memory row */
+    constexpr int RL = NT / NCP;                      /* row lanes of the vertical pass */
+    extern __shared__ double sm[];
+    double* const S = sm;                             /* [SR][SC]  Y of the source footprint */
+    double* const T = sm + p.SR * SC;                 /* [TH][SC]  Y after the vertical pass (FP32 values, widened) */
+    __shared__ int s_red[8][4];
+    __shared__ int s_vl[TH];
+    __shared__ double s_vw[TH * WY];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned x0 = blockIdx.x * TW, gy0 = p.e0 + blockIdx.y * TH;
+    const int ny = (int)min((unsigned)TH, p.e1 - gy0), nx = (int)min((unsigned)TW, p.ow - x0);
+
+    /* ---- 0. footprint of the tile: rows [rlo, rlo+nr), columns [clo, clo+nc) with clo, nc even; chroma region inside it */
+    {
+        int lo = INT_MAX, hi = -1, clo_ = INT_MAX, chi_ = -1;
+        if (warp < 4) {                               /* columns: the horizontal tables of this tile's nx destination columns */
+            if (tid < nx) {
+                const int a = __ldg(p.hyl + x0 + tid), b = __ldg(p.hcl + x0 + tid);
+                lo = min(a, b); hi = max(a + WY, b + 2); clo_ = b; chi_ = b + 2;
+            }
+        } else if (warp == 4) {                       /* rows */
+            if (lane < ny) {
+                const int a = __ldg(p.vyl + gy0 + lane), b = __ldg(p.vcl + gy0 + lane);
+                lo = min(a, b); hi = max(a + WY, b + 2); clo_ = b; chi_ = b + 2;
+                s_vl[lane] = a;
+            }
+        }
+        if (warp < 5) {
+            lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+            clo_ = __reduce_min_sync(0xffffffffu, clo_); chi_ = __reduce_max_sync(0xffffffffu, chi_);
+            if (lane == 0) { s_red[warp][0] = lo; s_red[warp][1] = hi; s_red[warp][2] = clo_; s_red[warp][3] = chi_; }
+        }
+        for (int i = tid; i < ny * WY; i += NT) s_vw[i] = __ldg(p.vyw + (size_t)gy0 * WY + i);
+    }
+    __syncthreads();
+    int clo = min(min(s_red[0][0], s_red[1][0]), min(s_red[2][0], s_red[3][0]));
+    int chi = max(max(s_red[0][1], s_red[1][1]), max(s_red[2][1], s_red[3][1]));
+    int cc0 = min(min(s_red[0][2], s_red[1][2]), min(s_red[2][2], s_red[3][2]));      /* chroma columns handed over by this tile */
+    int cc1 = max(max(s_red[0][3], s_red[1][3]), max(s_red[2][3], s_red[3][3]));
+    const int rlo = s_red[4][0], nr = s_red[4][1] - rlo, cr0 = s_red[4][2], cr1 = s_red[4][3];
+    clo &= ~1; chi = (chi + 1) & ~1; cc0 &= ~1; cc1 = (cc1 + 1) & ~1;
+    const int nc = chi - clo, ncp = nc >> 1;
+
+    /* ---- 1. colour-in of the footprint (reference converImgU8toYCbCr, src/libsrcnn.cpp:233-272): a thread keeps ONE column
+     * pair and walks down the rows in steps of RL, so everything but the row is loop-invariant.  All of a thread's source
+     * words (at most NI rows) are requested before the first one is used: the stage is bound by load latency otherwise */
+    {
+        constexpr int NI = 4;                                     /* rows per thread: nr <= NI * RL (checked on the host) */
+        const int cp = tid % NCP, rl = tid / NCP;
+        if (rl < RL && cp < ncp) {
+            const int col = clo + 2 * cp;
+            const bool ccol = col >= cc0 && col < cc1;
+            const uint32_t pix0 = (uint32_t)(rlo + rl - (int)p.src_row0) * p.w + (uint32_t)col;    /* (fits: checked on the host) */
+            const uint32_t pstep = (uint32_t)RL * p.w;
+            uint32_t raw[NI][3];
+            #pragma unroll
+            for (int k = 0; k < NI; k++)
+                if (rl + k * RL < nr) load_raw2<D>(f_src + (size_t)(pix0 + k * pstep) * D, raw[k]);
+            #pragma unroll
+            for (int k = 0; k < NI; k++) {
+                const int r = rl + k * RL;
+                if (r < nr) {
+                    float c[2][D];
+                    unpack_px2<D>(raw[k], c);
+                    float y0, y1, cb0, cb1, cr0_, cr1_;
+                    ycbcr_of(c[0][0], c[0][1], c[0][2], y0, cb0, cr0_);
+                    ycbcr_of(c[1][0], c[1][1], c[1][2], y1, cb1, cr1_);
+                    *reinterpret_cast<double2*>(S + r * SC + 2 * cp) = make_double2(widen(y0), widen(y1));
+                    const int row = rlo + r;
+                    if (ccol && row >= cr0 && row < cr1) {
+                        /* neighbouring tiles' regions overlap by a row / column pair: they store identical values (benign) */
+                        float* q = f_csrc + (pix0 + k * pstep);
+                        *reinterpret_cast<float2*>(q) = make_float2(cb0, cb1);
+                        *reinterpret_cast<float2*>(q + p.csrc_stride) = make_float2(cr0_, cr1_);
+                        if (NC == 3) *reinterpret_cast<float2*>(q + 2 * p.csrc_stride) = make_float2(c[0][D - 1], c[1][D - 1]);
+                    }
+                }
+            }
+        }
+    }
+    /* this thread's column pair of the horizontal table (global loads overlap the barrier) */
+    const int j = tid & (TW / 2 - 1), rbeg = (tid / (TW / 2)) * (TH / (NT / (TW / 2)));
+    constexpr int RPT2 = TH / (NT / (TW / 2));        /* rows per thread in the horizontal pass */
+    const unsigned gx = x0 + 2 * j;
+    const bool col_ok = 2 * j < nx;
+    double wa[WY], wb[WY + 1];
+    int o[WY + 1];
+    if (col_ok) {
+        const int la = __ldg(p.hyl + gx), lb = __ldg(p.hyl + gx + 1);     /* lb - la is 0 or 1 (checked on the host) */
+        #pragma unroll
+        for (int i = 0; i < WY; i++) wa[i] = __ldg(p.hyw + (size_t)gx * WY + i);
+        /* the second column reads the same WY + 1 samples with its weights shifted by lb - la (a zero weight on the sample it
+         * does not use: fma(0, v, acc) == acc for the finite v of an initialised footprint) */
+        double t[WY];
+        #pragma unroll
+        for (int i = 0; i < WY; i++) t[i] = __ldg(p.hyw + (size_t)(gx + 1) * WY + i);
+        const bool sh = lb != la;
+        wb[0] = sh ? 0.0 : t[0];
+        #pragma unroll
+        for (int i = 1; i < WY; i++) wb[i] = sh ? t[i - 1] : t[i];
+        wb[WY] = sh ? t[WY - 1] : 0.0;
+        #pragma unroll
+        for (int i = 0; i <= WY; i++) o[i] = min(la - clo + i, nc - 1);
+    }
+    __syncthreads();
+
+    /* ---- 2. vertical pass, shared -> shared (reference verticalFilter, src/frawscale.cpp:335-385): thread = column pair x row lane */
+    {
+        const int cp = tid % NCP, rl = tid / NCP;
+        if (rl < RL && cp < ncp) {
+            const double2* const S2 = reinterpret_cast<const double2*>(S) + cp;
+            double2* const T2 = reinterpret_cast<double2*>(T) + cp;
+            /* two destination rows per step: four independent accumulator chains hide the FP64 / shared-memory latency */
+            #pragma unroll 1
+            for (int y = rl; y < ny; y += 2 * RL) {
+                const int y2 = min(y + RL, ny - 1);                /* (the last step may repeat row ny-1: same value stored twice) */
+                const double2* sa = S2 + (s_vl[y] - rlo) * NCP;
+                const double2* sb = S2 + (s_vl[y2] - rlo) * NCP;
+                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+                #pragma unroll
+                for (int i = 0; i < WY; i++) {
+                    const double wa_ = s_vw[y * WY + i], wb_ = s_vw[y2 * WY + i];
+                    const double2 va = sa[i * NCP], vb = sb[i * NCP];
+                    a0 = mac<FMA>(a0, wa_, va.x); a1 = mac<FMA>(a1, wa_, va.y);
+                    b0 = mac<FMA>(b0, wb_, vb.x); b1 = mac<FMA>(b1, wb_, vb.y);
+                }
+                /* the reference's FP32 intermediate plane */
+                T2[y * NCP] = make_double2((double)__double2float_rn(a0), (double)__double2float_rn(a1));
+                T2[y2 * NCP] = make_double2((double)__double2float_rn(b0), (double)__double2float_rn(b1));
+            }
+        }
+    }
+    __syncthreads();
+
+    /* ---- 3. horizontal pass, shared -> registers -> global (reference horizontalFilter, src/frawscale.cpp:288-332) */
+    const int ybase = (int)gy0 - p.strip_row0 + kHaloRows;       /* conv-input plane row of tile row 0 */
+    if (col_ok) {
+        const int nrows = max(0, min(ny - rbeg, RPT2));
+        const double* t = T + rbeg * SC;
+        __half2* o16 = f_y16 ? reinterpret_cast<__half2*>(f_y16 + (size_t)(ybase + rbeg) * p.pitch + gx + kY16PadL) : nullptr;
+        float2* o32 = p.write_y32 ? reinterpret_cast<float2*>(p.planes + (size_t)(gy0 + rbeg - p.e0) * p.ow + gx) : nullptr;
+        const int pitch2 = p.pitch >> 1; const unsigned ow2 = p.ow >> 1;
+        auto body = [&](int r) {
+            double v[WY + 1];
+            #pragma unroll
+            for (int i = 0; i <= WY; i++) v[i] = t[r * SC + o[i]];
+            double a = 0.0, b = 0.0;
+            #pragma unroll
+            for (int i = 0; i < WY; i++) a = mac<FMA>(a, wa[i], v[i]);
+            #pragma unroll
+            for (int i = 0; i <= WY; i++) b = mac<FMA>(b, wb[i], v[i]);     /* (0 * v adds +-0: a no-op on a sum that starts at +0) */
+            const float fa = __double2float_rn(a), fb = __double2float_rn(b);
+            if (o16) o16[r * pitch2] = __floats2half2_rn(fa, fb);
+            if (o32) o32[(size_t)r * ow2] = make_float2(fa, fb);
+        };
+        if (nrows == RPT2) {
+            #pragma unroll
+            for (int r = 0; r < RPT2; r++) body(r);
+        } else {
+            #pragma unroll 1
+            for (int r = 0; r < nrows; r++) body(r);
+        }
+    }
+    if (!f_y16) return;
+    __syncthreads();            /* the tile's conv-input values are visible to the whole CTA */
+
+    /* ---- 3b. replicate padding of the conv-input plane around the image (border tiles only), as in prep_kernel */
+    const bool first_col = (x0 == 0), last_col = (x0 + nx == p.ow);
+    if (first_col || last_col) {
+        const int c_hi = (int)p.ow + kY16PadL, npad_r = last_col ? p.pitch - c_hi : 0, npad_l = first_col ? kY16PadL : 0;
+        const int per_row = npad_l + npad_r;
+        for (int idx = tid; idx < ny * per_row; idx += NT) {
+            const int r = idx / per_row, k = idx - r * per_row;
+            __half* row = f_y16 + (size_t)(ybase + r) * p.pitch;
+            if (k < npad_l) row[k] = row[kY16PadL];
+            else            row[c_hi + (k - npad_l)] = row[c_hi - 1];
+        }
+        __syncthreads();
+    }
+    const bool top = (gy0 == 0) && ybase > 0, bottom = (gy0 + ny == p.oh) && (ybase + ny < p.y16_rows);
+    if (top || bottom) {
+        const int ca = first_col ? 0 : (int)x0 + kY16PadL, cb = last_col ? p.pitch : (int)x0 + nx + kY16PadL;
+        const int span = cb - ca;
+        if (top) {
+            const __half* from = f_y16 + (size_t)ybase * p.pitch + ca;
+            for (int idx = tid; idx < ybase * span; idx += NT) {
+                const int r = idx / span, c = idx - r * span;
+                f_y16[(size_t)r * p.pitch + ca + c] = from[c];
+            }
+        }
+        if (bottom) {
+            const int rb = ybase + ny, nrep = p.y16_rows - rb;
+            const __half* from = f_y16 + (size_t)(rb - 1) * p.pitch + ca;
+            for (int idx = tid; idx < nrep * span; idx += NT) {
+                const int r = idx / span, c = idx - r * span;
+                f_y16[(size_t)(rb + r) * p.pitch + ca + c] = from[c];
+            }
+        }
+    }
+}
+
 /* dynamic shared memory of one CTA (bytes) */
 inline size_t prep_smem(int d, int cm, int SR, int SC, bool csrc)
 {
@@ -459,6 +725,54 @@ int max_footprint(const int* ly, int wy, const int* lc, int wc, unsigned d0, uns
     return best;
 }
 
+
+
+/* host-side: largest even-aligned column extent / row extent of a tile footprint */
+int max_footprint_even(const int* ly, int wy, const int* lc, int wc, unsigned d0, unsigned d1, unsigned tile)
+{
+    int best = 0;
+    for (unsigned a = d0; a < d1; a += tile) {
+        const unsigned b = std::min(d1, a + tile);
+        int lo = INT_MAX, hi = -1;
+        for (unsigned u = a; u < b; u++) {
+            lo = std::min(lo, std::min(ly[u], lc[u]));
+            hi = std::max(hi, std::max(ly[u] + wy, lc[u] + wc));
+        }
+        best = std::max(best, ((hi + 1) & ~1) - (lo & ~1));
+    }
+    return best;
+}
+
+template <int D, int WY, bool FMA>
+int launch_prep2(const PrepParams& p, dim3 grid, cudaStream_t s)
+{
+    constexpr int SC = 72;
+    static std::atomic<bool> configured[kMaxDevices];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return 0; }
+    const size_t smem = ((size_t)p.SR + TH) * SC * sizeof(double);
+    if (!configured[dev].load(std::memory_order_acquire)) {
+        if (cudaFuncSetAttribute(prep2_kernel<D, WY, SC, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
+            cudaGetLastError(); return 0;
+        }
+        configured[dev].store(true, std::memory_order_release);
+    }
+    if (smem > 100 * 1024) return 0;
+    prep2_kernel<D, WY, SC, FMA><<<grid, NT, smem, s>>>(p);
+    return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
+}
+
+template <int D, bool FMA>
+int launch_prep2_wy(const PrepParams& p, int wy, dim3 grid, cudaStream_t s)
+{
+    switch (wy) {
+        case 2:  return launch_prep2<D, 2, FMA>(p, grid, s);
+        case 4:  return launch_prep2<D, 4, FMA>(p, grid, s);
+        case 6:  return launch_prep2<D, 6, FMA>(p, grid, s);
+        default: return 0;
+    }
+}
+
 } // namespace
 
 bool prep_chroma_handover(const AxisTableDev& vc, const AxisTableDev& hc)
@@ -471,6 +785,48 @@ bool prep_supported(const AxisTableDev& vy, const AxisTableDev& vc, const AxisTa
     if (!vy.cleft || !vc.cleft || !hy.cleft || !hc.cleft) return false;
     if (vy.cwin != hy.cwin || (vy.cwin != 2 && vy.cwin != 4 && vy.cwin != 6)) return false;
     return vc.cwin == 2 && hc.cwin == 2;
+}
+
+/* host-side: every pair of adjacent destination columns (2j, 2j+1) starts its window at the same source column or one later */
+bool prep2_pairs_ok(const int* h_hyl, unsigned ow)
+{
+    if (ow & 1u) return false;
+    for (unsigned x = 0; x + 1 < ow; x += 2) {
+        const int dlt = h_hyl[x + 1] - h_hyl[x];
+        if (dlt != 0 && dlt != 1) return false;
+    }
+    return true;
+}
+
+int launch_prep2(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, unsigned ow, unsigned oh,
+                 unsigned e0, unsigned e1, float* y32, bool fused_mac, __half* y16, Y16Geom g, unsigned strip_row0,
+                 const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc,
+                 const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, bool pairs_ok, cudaStream_t s,
+                 float* csrc, size_t csrc_stride, unsigned nframes, size_t src_fstride, size_t y16_fstride, size_t csrc_fstride)
+{
+    if (!csrc || !pairs_ok || (w & 1u) || (ow & 1u) || (csrc_stride & 1u) || (csrc_fstride & 1u) || (d != 3 && d != 4)) return 0;
+    if (((uintptr_t)src & 7u) || ((src_fstride) & 7u) || ((uintptr_t)csrc & 7u)) return 0;
+    if (!prep_supported(vy, vc, hy, hc) || !prep_chroma_handover(vc, hc)) return 0;
+    if (nframes > 1 && y32) return 0;
+    if (y16 && ((g.pitch & 1) || ((uintptr_t)y16 & 3u) || (y16_fstride & 1u))) return 0;
+    if (y32 && (((uintptr_t)y32 & 7u))) return 0;
+    PrepParams p{};
+    p.src = src; p.w = w; p.src_row0 = src_row0; p.ow = ow; p.oh = oh; p.e0 = e0; p.e1 = e1;
+    p.planes = y32; p.plane_stride = 0; p.write_y32 = y32 ? 1 : 0;
+    p.y16 = y16; p.pitch = g.pitch; p.y16_rows = g.rows; p.strip_row0 = (int)strip_row0;
+    p.vyl = vy.cleft; p.vcl = vc.cleft; p.hyl = hy.cleft; p.hcl = hc.cleft;
+    p.vyw = vy.cw; p.vcw = vc.cw; p.hyw = hy.cw; p.hcw = hc.cw;
+    p.SR = max_footprint(h_vyl, vy.cwin, h_vcl, vc.cwin, e0, e1, TH);
+    p.SC = max_footprint_even(h_hyl, hy.cwin, h_hcl, hc.cwin, 0, ow, TW);
+    if (p.SC > 72 || p.SR > 28) return 0;                       /* prep2_kernel: SC = 72, at most 4 x 7 footprint rows */
+    if ((size_t)(oh ? (size_t)w * ((size_t)oh / 1 + 64) : 0) * 4 >= ((size_t)1 << 31)) return 0;       /* 32-bit pixel offsets (source rows <= oh) */
+    p.csrc = csrc; p.csrc_stride = csrc_stride;
+    p.src_fstride = src_fstride; p.y16_fstride = y16_fstride; p.csrc_fstride = csrc_fstride;
+    if ((size_t)oh * 8 >= (size_t)INT_MAX || (size_t)ow * 8 >= (size_t)INT_MAX) return 0;
+    dim3 grid((ow + TW - 1) / TW, (e1 - e0 + TH - 1) / TH, nframes ? nframes : 1);
+    if (grid.y > 65535u || grid.z > 65535u) return 0;
+    if (d == 3) return fused_mac ? launch_prep2_wy<3, true>(p, vy.cwin, grid, s) : launch_prep2_wy<3, false>(p, vy.cwin, grid, s);
+    return fused_mac ? launch_prep2_wy<4, true>(p, vy.cwin, grid, s) : launch_prep2_wy<4, false>(p, vy.cwin, grid, s);
 }
 
 int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, unsigned ow, unsigned oh,

@@ -113,6 +113,7 @@ struct TableDev {
     void* dev = nullptr;
     AxisTableDev view{};
     bool quads_ok = false;      /* compact form: 4 adjacent destination samples read <= 4 adjacent source samples (color.cu) */
+    bool pairs_ok = false;      /* compact form: the windows of destination samples 2j, 2j+1 start 0 or 1 apart (prep.cu: prep2_kernel) */
 };
 
 /* geometry of one pass restricted to a row strip */
@@ -141,6 +142,12 @@ struct srcnn_b200_ctx {
     cudaEvent_t ev[8] = {};
     int ev_alias[8] = { 0, 1, 2, 3, 4, 5, 6, 7 };   /* event that stands for stage boundary i (Stamp) */
     cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
+    /* asynchronous host passes (srcnn_b200_pass_host_async): call k uses device buffer set k & 1; ev_ak / ev_ao mark the end of
+     * the kernels / of the downloads of the last call on that set */
+    cudaEvent_t ev_ak[2] = {}, ev_ao[2] = {};
+    bool async_used[2] = { false, false };
+    unsigned long long async_seq = 0;
+    int async_rc = 0;
     float ms[7] = {};
     unsigned long long launches = 0;
     std::string err;
@@ -151,7 +158,9 @@ struct srcnn_b200_ctx {
     std::vector<cudaEvent_t> pipe_ev;         /* 3 per sub-strip: uploaded, computed, downloaded                      */
     HostCopier copier;
     bool fuse_front = true;                   /* one-kernel front end (SRCNN_B200_FUSE=0: the separate kernels)       */
-    bool keep_planes = false;                 /* also write the FP32 interpolated Y plane in tensor mode (getters)    */
+    int keep_planes = 0;                      /* tensor mode: 1 = also write the FP32 interpolated Y and the output-size chroma planes
+                                                 (getters; first-generation front end), 2 = the FP32 Y plane only, product route kept */
+    bool prep2 = true;                        /* second-generation front end on the x2 hand-over route (SRCNN_B200_PREP2=0: off) */
     bool last_has_y32 = false;
     bool last_has_chroma = true;              /* output-size Cb / Cr / A planes of the last pass exist (getters 1-3)   */
     bool group_frames = true;                 /* batches: one conv launch per group of small frames (SRCNN_B200_GROUP=0) */
@@ -252,6 +261,7 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     t->view.pow2pair = h.pow2pair ? 1 : 0;
     t->view.pack2 = pbytes ? base + poff : nullptr;
     t->quads_ok = h.compact && h.cwin == 2 && color_out_up_quads_ok(h.cleft.data(), dst);
+    t->pairs_ok = h.compact && prep2_pairs_ok(h.cleft.data(), dst);
     ctx->tables[key] = t;
     *out = t;
     return 0;
@@ -334,17 +344,27 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
 
     Stamp st(ctx);
     /* 1.-4. front end.  Preferred: ONE kernel (colour-in + both resampling passes + conv-input pack, prep.cu) */
-    const bool y32 = !tensor || ctx->keep_planes;
+    const bool y32 = !tensor || ctx->keep_planes != 0;
     bool fused = false, chroma_up = false;
     const size_t ps_csrc = al((size_t)srows * p.w);
     if (ctx->fuse_front && !p.hfirst && p.need_h && p.need_v && prep_supported(vy->view, vc->view, hy->view, hc->view)) {
         /* x2-type magnification: Cb / Cr / A stay at source resolution and are resampled inside colour-out (the output-size
          * chroma planes then never exist -- unless the plane getters were asked to keep them) */
-        chroma_up = ctx->chroma_up && !ctx->keep_planes && !(tensor && ctx->fuse_color) && prep_chroma_handover(vc->view, hc->view) && (p.ow % 4) == 0 &&
+        chroma_up = ctx->chroma_up && ctx->keep_planes != 1 && !(tensor && ctx->fuse_color) && prep_chroma_handover(vc->view, hc->view) && (p.ow % 4) == 0 &&
                     hc->quads_ok && ((uintptr_t)d_out % (p.d == 4 ? 16 : 4)) == 0 &&
                     (!d_conv || ((uintptr_t)d_conv % 4) == 0);
         if (chroma_up) CK(ctx->chroma_src.ensure(ps_csrc * (p.d - 1) * sizeof(float)));
-        const int lp = launch_prep(d_src, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, P_dst, ps_dst, y32,
+        int lp = 0;
+        if (chroma_up && ctx->prep2)
+            /* product route: second-generation kernel; one double FMA per tap in tensor mode, the reference's separately rounded
+             * multiply and add in bit-exact mode */
+            lp = launch_prep2(d_src, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, y32 ? P_dst : nullptr, tensor,
+                              tensor ? static_cast<__half*>(ctx->y16.p) : nullptr, g, p.r0,
+                              vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
+                              hy->host.cleft.data(), hc->host.cleft.data(), hy->pairs_ok, s,
+                              static_cast<float*>(ctx->chroma_src.p), ps_csrc);
+        if (lp == 0)
+          lp = launch_prep(d_src, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, P_dst, ps_dst, y32,
                                    tensor ? static_cast<__half*>(ctx->y16.p) : nullptr, g, p.r0,
                                    vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
                                    hy->host.cleft.data(), hc->host.cleft.data(), s,
@@ -412,7 +432,7 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
             col.al = p.d == 4 ? P_dst + 3 * ps_dst + off : nullptr;
             col.rgb = d_out; col.conv8 = d_conv; col.d = p.d;
         }
-        ctx->last_has_yp = !fuse_out || ctx->keep_planes;
+        ctx->last_has_yp = !fuse_out || ctx->keep_planes != 0;
         if (launch_conv_tc(ctx->tc, static_cast<const __half*>(ctx->y16.p), g, p.ow, p.oh, ctx->last_has_yp ? Yp : nullptr,
                            p.r0, p.r1, ctx->num_sms, s, fuse_out ? &col : nullptr)) {
             ctx->err = std::string("conv_tc: ") + conv_tc_error(ctx->tc);
@@ -464,7 +484,7 @@ int collect_timing(srcnn_b200_ctx* ctx)
  * front end, chroma resampled inside colour-out; anything else runs frame by frame through run_pass. */
 unsigned group_size(const srcnn_b200_ctx* ctx, const Plan& p, unsigned n)
 {
-    if (ctx->conv_mode != SRCNN_B200_CONV_TENSOR || !ctx->fuse_front || !ctx->chroma_up || ctx->keep_planes ||
+    if (ctx->conv_mode != SRCNN_B200_CONV_TENSOR || !ctx->fuse_front || !ctx->chroma_up || ctx->keep_planes != 0 ||
         ctx->fuse_color || !ctx->group_frames) return 1;
     if (p.hfirst || !p.need_h || !p.need_v || (p.ow % 4) || p.r0 != 0 || p.r1 != p.oh) return 1;
     const size_t px = (size_t)p.ow * p.oh;
@@ -499,7 +519,13 @@ int run_group(srcnn_b200_ctx* ctx, Plan& p, unsigned G, const uint8_t* d_src, ui
     float* Yp = static_cast<float*>(ctx->yprime.p);
     cudaStream_t s = ctx->stream;
     Stamp st(ctx);                                                  /* timings then describe the whole group */
-    const int lp = launch_prep(d_src + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, 0, false,
+    int lp = 0;
+    if (ctx->prep2)
+        lp = launch_prep2(d_src + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, true, Y16, g, p.r0,
+                          vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
+                          hy->host.cleft.data(), hc->host.cleft.data(), hy->pairs_ok, s, CS, ps_csrc, G, ib, y16_f, csrc_f);
+    if (lp == 0)
+      lp = launch_prep(d_src + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, 0, false,
                                Y16, g, p.r0, vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(),
                                vc->host.cleft.data(), hy->host.cleft.data(), hc->host.cleft.data(), s, CS, ps_csrc,
                                G, ib, y16_f, csrc_f);
@@ -562,6 +588,7 @@ int srcnn_b200_create(int device, srcnn_b200_ctx** out)
     if (const char* e = getenv("SRCNN_B200_FUSE_COLOR")) ctx->fuse_color = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_CHROMA_UP")) ctx->chroma_up = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_GROUP")) ctx->group_frames = atoi(e) != 0;
+    if (const char* e = getenv("SRCNN_B200_PREP2")) ctx->prep2 = atoi(e) != 0;
     {
         unsigned nt = std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2));
         if (const char* e = getenv("SRCNN_B200_COPY_THREADS")) nt = (unsigned)std::max(1, atoi(e));
@@ -574,7 +601,9 @@ int srcnn_b200_create(int device, srcnn_b200_ctx** out)
     for (int i = 0; ok && i < 2; i++)
         ok = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_ak[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_ao[i], cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = conv_exact_init() == 0;
     if (ok) ok = conv_tc_create(&ctx->tc) == 0;
     if (!ok) {
@@ -599,6 +628,8 @@ void srcnn_b200_destroy(srcnn_b200_ctx* ctx)
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
         if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
         if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+        if (ctx->ev_ak[i]) cudaEventDestroy(ctx->ev_ak[i]);
+        if (ctx->ev_ao[i]) cudaEventDestroy(ctx->ev_ao[i]);
     }
     ctx->chroma_src.release();
     ctx->planes_src.release(); ctx->tmp.release(); ctx->planes_dst.release(); ctx->y16.release(); ctx->yprime.release();
@@ -629,22 +660,40 @@ void srcnn_b200_output_dims(unsigned w, unsigned h, float multiply, unsigned* ow
 }
 
 /* step-scale schedule (src/libsrcnn.cpp:980-1061): factors[] of the passes that actually run */
-static int step_schedule(unsigned w, float multiply, float* factors, int maxn)
+/* *conv_pass: only the pass with cnt + 1 == repeat receives the caller's convbuff (:1024-1028); when the loop breaks before it
+ * (remaining factor exactly 1, e.g. x8 = x2 x2 x2 then x1) the reference never produces a convolution plane */
+static int step_schedule(unsigned w, float multiply, float* factors, int maxn, int* conv_pass = nullptr)
 {
     const float lf = fmodf(multiply, 2.f);
     int repeat = (int)(multiply / 2.f);
     if (lf > 0.f) repeat++;
     unsigned sw = w; int n = 0;
+    if (conv_pass) *conv_pass = 0;
     for (int cnt = 0; cnt < repeat && n < maxn; cnt++) {
         float m = 2.0f;
         if (cnt + 1 == repeat) {
             m = ((float)w * multiply) / (float)sw;
             if (m == 0.f || m == 1.0f) break;
+            if (conv_pass) *conv_pass = 1;
         }
         factors[n++] = m;
         if (repeat > 1) sw = (unsigned)((float)sw * m);
     }
     return n;
+}
+
+int srcnn_b200_step_factors(unsigned w, float multiply, float* factors, int maxn)
+{
+    if (!factors || maxn <= 0) return SRCNN_B200_EINVAL;
+    return step_schedule(w, multiply, factors, maxn);
+}
+
+int srcnn_b200_process_has_conv(unsigned w, float multiply, int stepscale)
+{
+    if (!stepscale) return 1;
+    float f[64]; int cp = 0;
+    step_schedule(w, multiply, f, 64, &cp);
+    return cp;
 }
 
 int srcnn_b200_process_dims(unsigned w, unsigned h, float multiply, int stepscale, unsigned* ow, unsigned* oh)
@@ -712,7 +761,7 @@ static void drain_streams(srcnn_b200_ctx* ctx)
 
 static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
                                float multiply, int filter, unsigned row0, unsigned row1,
-                               uint8_t* out_rows, uint8_t* conv_rows)
+                               uint8_t* out_rows, uint8_t* conv_rows, bool async = false)
 {
     if (!ctx || !src || !out_rows) return SRCNN_B200_EINVAL;
     Plan p; int rc = make_plan(w, h, d, multiply, filter, row0, row1, p);
@@ -744,16 +793,25 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
     }
     const unsigned S0 = sp[0].s0, S1 = sp[nstrips - 1].s1;
     const size_t src_row_bytes = (size_t)w * d;
-    CK(ctx->src8[0].ensure((size_t)(S1 - S0) * src_row_bytes));
-    CK(ctx->out8[0].ensure(out_bytes));
-    if (conv_rows) CK(ctx->conv8[0].ensure(conv_bytes));
-    uint8_t* d_src = static_cast<uint8_t*>(ctx->src8[0].p);
-    uint8_t* d_out = static_cast<uint8_t*>(ctx->out8[0].p);
-    uint8_t* d_conv = conv_rows ? static_cast<uint8_t*>(ctx->conv8[0].p) : nullptr;
+    /* asynchronous calls alternate between two device buffer sets, so call k+1 uploads while call k computes / downloads;
+     * the blocking call always uses set 0 (and has drained everything before it returns) */
+    const int bs = async ? (int)(ctx->async_seq & 1) : 0;
+    if (async && ctx->async_used[bs]) {
+        /* set `bs` was last used two calls ago: its kernels must have read the source, its downloads must have left */
+        CK(cudaStreamWaitEvent(ctx->stream_in, ctx->ev_ak[bs], 0));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ao[bs], 0));
+    }
+    /* (a growing buffer is re-allocated: cudaFree waits for the device, so earlier asynchronous work is not disturbed) */
+    CK(ctx->src8[bs].ensure((size_t)(S1 - S0) * src_row_bytes));
+    CK(ctx->out8[bs].ensure(out_bytes));
+    if (conv_rows) CK(ctx->conv8[bs].ensure(conv_bytes));
+    uint8_t* d_src = static_cast<uint8_t*>(ctx->src8[bs].p);
+    uint8_t* d_out = static_cast<uint8_t*>(ctx->out8[bs].p);
+    uint8_t* d_conv = conv_rows ? static_cast<uint8_t*>(ctx->conv8[bs].p) : nullptr;
 
     /* pageable destination: DMA into pinned staging slots, worker threads move the rows on (a cudaMemcpy straight
      * into pageable memory is staged by the driver in small chunks and blocks the pipeline) */
-    const bool stage = ctx->stage_pageable && nstrips > 1 && !host_is_pinned(out_rows);
+    const bool stage = !async && ctx->stage_pageable && nstrips > 1 && !host_is_pinned(out_rows);
     size_t slot_bytes = 0;
     if (stage) {
         for (unsigned i = 0; i < nstrips; i++)
@@ -761,10 +819,12 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
         slot_bytes = (slot_bytes + 4095) / 4096 * 4096;
         CK(ctx->pin_out[0].ensure(slot_bytes * kStageSlots));
     }
-    CK(ensure_pipe_events(ctx, nstrips));
+    /* events of the sub-strip pipeline; an asynchronous call on buffer set 1 uses the second half of the event pool */
+    const unsigned ev0 = (unsigned)bs * 3u * kMaxPipeStrips;
+    CK(ensure_pipe_events(ctx, 2 * kMaxPipeStrips));
 
     auto drain = [&](unsigned j) -> int {      /* staging slot j % kStageSlots -> caller's rows */
-        CK(cudaEventSynchronize(ctx->pipe_ev[3 * j + 2]));
+        CK(cudaEventSynchronize(ctx->pipe_ev[ev0 + 3 * j + 2]));
         const unsigned char* slot = static_cast<unsigned char*>(ctx->pin_out[0].p) + (size_t)(j % kStageSlots) * slot_bytes;
         const size_t ob = (size_t)(sp[j].r1 - sp[j].r0) * row_bytes, off = (size_t)(sp[j].r0 - row0);
         ctx->copier.copy(out_rows + off * row_bytes, slot, ob);
@@ -774,7 +834,7 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
 
     unsigned uploaded = S0;
     for (unsigned i = 0; i < nstrips; i++) {
-        cudaEvent_t ev_in = ctx->pipe_ev[3 * i], ev_k = ctx->pipe_ev[3 * i + 1], ev_out = ctx->pipe_ev[3 * i + 2];
+        cudaEvent_t ev_in = ctx->pipe_ev[ev0 + 3 * i], ev_k = ctx->pipe_ev[ev0 + 3 * i + 1], ev_out = ctx->pipe_ev[ev0 + 3 * i + 2];
         if (sp[i].s1 > uploaded) {
             CK(cudaMemcpyAsync(d_src + (size_t)(uploaded - S0) * src_row_bytes, src + (size_t)uploaded * src_row_bytes,
                                (size_t)(sp[i].s1 - uploaded) * src_row_bytes, cudaMemcpyHostToDevice, ctx->stream_in));
@@ -799,6 +859,14 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
         }
         CK(cudaEventRecord(ev_out, ctx->stream_out));
     }
+    if (async) {
+        /* nothing is waited for: the caller's buffers are in use until srcnn_b200_wait */
+        CK(cudaEventRecord(ctx->ev_ak[bs], ctx->stream));
+        CK(cudaEventRecord(ctx->ev_ao[bs], ctx->stream_out));
+        ctx->async_used[bs] = true;
+        ctx->async_seq++;
+        return 0;
+    }
     if (stage)
         for (unsigned j = nstrips > kStageSlots ? nstrips - kStageSlots : 0; j < nstrips; j++)
             if ((rc = drain(j))) return rc;
@@ -812,9 +880,40 @@ int srcnn_b200_pass_host_rows(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned 
                               float multiply, int filter, unsigned row0, unsigned row1,
                               uint8_t* out_rows, uint8_t* conv_rows)
 {
+    if (ctx && (ctx->async_used[0] || ctx->async_used[1])) { const int w0 = srcnn_b200_wait(ctx); if (w0) return w0; }
     const int rc = pass_host_rows_impl(ctx, src, w, h, d, multiply, filter, row0, row1, out_rows, conv_rows);
     if (rc && ctx) drain_streams(ctx);
     return rc;
+}
+
+/* Stream-ordered, non-blocking variant: uploads, kernels and downloads are only ENQUEUED; src / out / conv
+ * must stay valid -- and should be pinned (srcnn_b200_host_alloc), a copy from / to pageable memory makes the call wait --
+ * until srcnn_b200_wait returns.  Up to two calls are in flight per context (two device buffer sets): the upload of call k+1
+ * overlaps the kernels and the download of call k. */
+int srcnn_b200_pass_host_async(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
+                               float multiply, int filter, uint8_t* out, uint8_t* conv)
+{
+    unsigned ow = 0, oh = 0;
+    if (!ctx || !w || !h || (d != 3 && d != 4)) return SRCNN_B200_EINVAL;
+    if ((float)w * multiply <= 0.f || (float)h * multiply <= 0.f) return SRCNN_B200_ESIZE;
+    srcnn_b200_output_dims(w, h, multiply, &ow, &oh);
+    if (!ow || !oh) return SRCNN_B200_ESIZE;
+    const int rc = pass_host_rows_impl(ctx, src, w, h, d, multiply, filter, 0, oh, out, conv, true);
+    if (rc) { drain_streams(ctx); ctx->async_used[0] = ctx->async_used[1] = false; }
+    return rc;
+}
+
+int srcnn_b200_wait(srcnn_b200_ctx* ctx)
+{
+    if (!ctx) return SRCNN_B200_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream_in);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream_out);
+    ctx->async_used[0] = ctx->async_used[1] = false;
+    if (e != cudaSuccess) { drain_streams(ctx); return fail_cuda(ctx, e, "srcnn_b200_wait"); }
+    collect_timing(ctx);
+    return 0;
 }
 
 int srcnn_b200_pass_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
@@ -836,9 +935,10 @@ static int process_host_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w
     if ((float)w * multiply <= 0.f || (float)h * multiply <= 0.f) return SRCNN_B200_ESIZE;
     if (!stepscale) return srcnn_b200_pass_host(ctx, src, w, h, d, multiply, filter, out, conv);
 
-    float f[64];
-    const int n = step_schedule(w, multiply, f, 64);
+    float f[64]; int conv_pass = 0;
+    const int n = step_schedule(w, multiply, f, 64, &conv_pass);
     if (n == 0) return SRCNN_B200_ENOTHING;
+    if (!conv_pass) conv = nullptr;           /* the reference produces no convolution plane for this factor: `conv` stays untouched */
     if (n == 1) return srcnn_b200_pass_host(ctx, src, w, h, d, f[0], filter, out, conv);
     if (!out) return SRCNN_B200_EINVAL;
     /* chain: 8-bit RGB(A) intermediates stay in HBM (the reference round-trips them through host buffers,
@@ -880,6 +980,7 @@ static int process_host_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w
 int srcnn_b200_process_host(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned w, unsigned h, unsigned d,
                             float multiply, int filter, int stepscale, uint8_t* out, uint8_t* conv)
 {
+    if (ctx && (ctx->async_used[0] || ctx->async_used[1])) { const int w0 = srcnn_b200_wait(ctx); if (w0) return w0; }
     const int rc = process_host_impl(ctx, src, w, h, d, multiply, filter, stepscale, out, conv);
     if (rc && rc != SRCNN_B200_ENOTHING && ctx) drain_streams(ctx);
     return rc;
@@ -969,6 +1070,7 @@ static int batch_host_impl(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned 
 int srcnn_b200_batch_host(srcnn_b200_ctx* ctx, const uint8_t* frames, unsigned n, unsigned w, unsigned h,
                           unsigned d, float multiply, int filter, uint8_t* out, uint8_t* conv)
 {
+    if (ctx && (ctx->async_used[0] || ctx->async_used[1])) { const int w0 = srcnn_b200_wait(ctx); if (w0) return w0; }
     const int rc = batch_host_impl(ctx, frames, n, w, h, d, multiply, filter, out, conv);
     if (rc && ctx) drain_streams(ctx);
     return rc;
@@ -1003,7 +1105,15 @@ int srcnn_b200_get_plane(srcnn_b200_ctx* ctx, int which, float* host, size_t cap
     return 0;
 }
 
-int srcnn_b200_set_keep_planes(srcnn_b200_ctx* ctx, int on) { if (!ctx) return SRCNN_B200_EINVAL; ctx->keep_planes = on != 0; return 0; }
+int srcnn_b200_set_copy_threads(srcnn_b200_ctx* ctx, unsigned n)
+{
+    if (!ctx || n == 0 || n > 64) return SRCNN_B200_EINVAL;
+    ctx->copier.stop();
+    ctx->copier.start(n - 1);
+    return 0;
+}
+
+int srcnn_b200_set_keep_planes(srcnn_b200_ctx* ctx, int on) { if (!ctx) return SRCNN_B200_EINVAL; ctx->keep_planes = on == 2 ? 2 : (on != 0); return 0; }
 int srcnn_b200_set_timing(srcnn_b200_ctx* ctx, int on) { if (!ctx) return SRCNN_B200_EINVAL; ctx->timing = on != 0; return 0; }
 int srcnn_b200_last_timings(srcnn_b200_ctx* ctx, float* ms7)
 {

@@ -107,6 +107,10 @@ CASES = [
     dict(id="smooth-bilinear-x2.5", kind="smooth", h=41, w=67, d=4, m=2.5, f=S.BILINEAR, s=False),
     dict(id="step-x3", kind="smooth", h=30, w=44, d=3, m=3.0, f=S.BICUBIC, s=True),
     dict(id="step-x4-rgba", kind="uniform", h=20, w=28, d=4, m=4.0, f=S.BILINEAR, s=True),
+    dict(id="step-x6", kind="uniform", h=14, w=18, d=3, m=6.0, f=S.BICUBIC, s=True),
+    # x8 = x2 x2 x2, then the remaining factor is 1: the loop breaks before the pass that would receive convbuff, so the
+    # reference produces NO convolution plane (src/libsrcnn.cpp:1003-1028)
+    dict(id="step-x8-no-conv-plane", kind="smooth", h=10, w=12, d=3, m=8.0, f=S.BICUBIC, s=True),
     dict(id="const0", kind="const0", h=24, w=24, d=3, m=2.0, f=S.BICUBIC, s=False),
     dict(id="const255", kind="const255", h=24, w=24, d=4, m=2.0, f=S.BICUBIC, s=False),
     dict(id="tiny-1x1", kind="uniform", h=1, w=1, d=3, m=2.0, f=S.BICUBIC, s=False),
@@ -131,7 +135,9 @@ def test_process_matches_oracle(ctx, case, mode):
     rc, out, conv = ctx.process(img, case["m"], case["f"], case["s"], True)
     assert rc == rc_o
     _check_u8("rgb", out, out_o, mode[0] == "exact")
-    _check_u8("conv", conv, conv_o, mode[0] == "exact")
+    assert (conv is None) == (conv_o is None)
+    if conv_o is not None:
+        _check_u8("conv", conv, conv_o, mode[0] == "exact")
 
 
 @pytest.mark.parametrize("filt", [S.BICUBIC, S.LANCZOS3, S.BSPLINE])
@@ -157,6 +163,21 @@ def test_interpolated_plane_and_network_output(ctx, filt):
     ctx.pass_host(img, 2.0, filt)
     _, gyp = ctx.get_plane(4, (120, 168))
     assert np.array_equal(gyp, yprime)
+    _, gy = ctx.get_plane(0, (120, 168))
+    assert np.array_equal(gy, y)                  # bit-exact mode: the product route's kernel with separately rounded mul / add
+    # the PRODUCT route's own front end (tensor mode, x2: one double FMA per tap): north-star gate 1e-5 relative on the plane;
+    # the fused form differs from the reference by < 2^-52 relative before the rounding to FP32, so nearly every sample is equal
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    ctx.set_keep_planes(2)
+    ctx.pass_host(img, 2.0, filt)
+    r0, gy = ctx.get_plane(0, (120, 168))
+    ctx.set_keep_planes(False)
+    assert r0 == 0
+    rel = np.abs(gy - y) / np.maximum(np.abs(y), 1.0)
+    assert rel.max() <= 1e-5
+    assert (gy != y).mean() < 1e-3
+    with pytest.raises(S.SrcnnError):
+        ctx.get_plane(1, (120, 168))              # the product route has no output-size chroma planes
 
 
 @pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
@@ -485,3 +506,122 @@ def test_c5_full_size_directly_against_oracle(ctx):
     assert rc == 0 and out.shape == (3240, 5760, 3)
     _check_u8("c5 rgb", out, want.reshape(3240, 5760, 3), False)
     _check_u8("c5 conv", conv, wconv.reshape(3240, 5760), False)
+
+
+# ---------------------------------------------------------------------------------------------- host-side drivers
+def test_async_passes_equal_blocking_passes(ctx):
+    """srcnn_b200_pass_host_async: several frames in flight on one context (pinned buffers), then one wait -- every result equals
+    the blocking call's; a blocking call issued while asynchronous work is pending waits for it first"""
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    frames = [O.synth("uniform", 120, 200, 3, 400 + i) for i in range(5)]
+    want = [ctx.pass_host(f, 2.0, S.BICUBIC, True) for f in frames]
+    h_in = [S.pinned_empty(f.shape) for f in frames]
+    h_out = [S.pinned_empty((240, 400, 3)) for _ in frames]
+    h_conv = [S.pinned_empty((240, 400)) for _ in frames]
+    for a, f in zip(h_in, frames):
+        a[...] = f
+    for o in h_out:
+        o[...] = 0
+    for i in range(5):
+        ctx.pass_host_async(h_in[i], 2.0, S.BICUBIC, h_out[i], h_conv[i])
+    ctx.wait()
+    for i in range(5):
+        assert np.array_equal(h_out[i], want[i][0]) and np.array_equal(h_conv[i], want[i][1]), "frame %d" % i
+    # pending asynchronous work + a blocking call on the same context
+    ctx.pass_host_async(h_in[0], 2.0, S.BICUBIC, h_out[0], None)
+    ctx.pass_host_async(h_in[1], 2.0, S.BICUBIC, h_out[1], None)
+    o, _ = ctx.pass_host(frames[2], 2.0, S.BICUBIC, False)
+    assert np.array_equal(o, want[2][0]) and np.array_equal(h_out[0], want[0][0]) and np.array_equal(h_out[1], want[1][0])
+    for a in h_in + h_out + h_conv:
+        S.lib().srcnn_b200_host_free(a.ctypes.data)
+
+
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+def test_single_process_multi_gpu_driver(ctx, mode, monkeypatch):
+    """srcnn_b200_multi: ONE host call cut into row strips / frame blocks over several per-device contexts and threads.  On a
+    one-GPU box the workers are three contexts on device 0 (the strip arithmetic, the threading and the per-context state are
+    the same); with more GPUs the first three devices.  Results must be bit-identical to the single-context call."""
+    monkeypatch.setenv("SRCNN_B200_MULTI_MIN_ROWS", "16")
+    n = S.device_count()
+    devs = [0, 1 % n, 2 % n]
+    m = S.Multi(devs, mode[1])
+    assert m.ndev == 3
+    ctx.set_conv_mode(mode[1])
+    try:
+        img = O.synth("uniform", 101, 150, 4, 50)
+        want, wconv = ctx.pass_host(img, 2.0, S.BICUBIC, True)
+        got, gconv = m.pass_host(img, 2.0, S.BICUBIC, True)
+        assert np.array_equal(got, want) and np.array_equal(gconv, wconv)
+        # the whole ProcessSRCNN semantics, step-scale chain included (every pass on all workers)
+        for mult, step in ((2.0, False), (3.0, True), (4.0, True), (1.5, True)):
+            rc1, o1, c1 = ctx.process(img[:40, :60], mult, S.LANCZOS3, step, True)
+            rc2, o2, c2 = m.process(img[:40, :60], mult, S.LANCZOS3, step, True)
+            assert rc1 == rc2 == 0 and np.array_equal(o1, o2) and np.array_equal(c1, c2), (mult, step)
+        assert m.process(img, 1.0, S.BICUBIC, True)[0] == S.ENOTHING
+        # frame batches: contiguous blocks of frames per worker
+        frames = np.stack([O.synth("uniform", 48, 64, 3, 60 + i) for i in range(7)])
+        bo, bc = ctx.batch(frames, 2.0, S.LANCZOS3, want_conv=True)
+        mo, mc = m.batch(frames, 2.0, S.LANCZOS3, want_conv=True)
+        assert np.array_equal(bo, mo) and np.array_equal(bc, mc)
+    finally:
+        m.close()
+
+
+def test_two_contexts_on_two_devices():
+    """one process, one context per GPU (function attributes are per device) -- needs two GPUs"""
+    if S.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    img = O.synth("uniform", 200, 300, 3, 9)
+    a, b = S.Context(0), S.Context(1)
+    try:
+        for mode in (S.CONV_TENSOR, S.CONV_EXACT):
+            a.set_conv_mode(mode); b.set_conv_mode(mode)
+            for filt, mult in ((S.BICUBIC, 2.0), (S.LANCZOS3, 2.0), (S.BSPLINE, 1.5)):
+                oa, ca = a.pass_host(img, mult, filt, True)
+                ob, cb = b.pass_host(img, mult, filt, True)
+                assert np.array_equal(oa, ob) and np.array_equal(ca, cb)
+    finally:
+        a.close(); b.close()
+
+
+def test_dropin_is_reentrant():
+    """concurrent ProcessSRCNN calls from several threads (the reference is re-entrant apart from its two settings,
+    src/libsrcnn.cpp:91-92): every call returns the result of a lone call"""
+    import threading
+    imgs = [O.synth("uniform", 90 + 10 * i, 130, 3 + (i & 1), 700 + i) for i in range(6)]
+    want = [S.process_srcnn(im, 2.0, S.BICUBIC, False, True) for im in imgs]
+    got = [None] * len(imgs)
+
+    def work(i):
+        for _ in range(3):
+            got[i] = S.process_srcnn(imgs[i], 2.0, S.BICUBIC, False, True)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(imgs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for i in range(len(imgs)):
+        assert got[i][0] == want[i][0] == 0
+        assert np.array_equal(got[i][1], want[i][1]) and np.array_equal(got[i][2], want[i][2]), "image %d" % i
+
+
+def test_dropin_over_several_devices():
+    """SRCNN_B200_DEVICES: the C++ drop-in call itself cut into row strips over the listed devices (a fresh process: the setting
+    is read once)"""
+    import subprocess, sys
+    n = S.device_count()
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, libsrcnn_b200 as S, oracle_lib as O\n"
+        "img = O.synth('uniform', 300, 200, 4, 5)\n"
+        "rc, out, conv = S.process_srcnn(img, 2.0, S.BICUBIC, False, True)\n"
+        "c = S.Context(0); w, wc = c.pass_host(img, 2.0, S.BICUBIC, True)\n"
+        "assert rc == 0 and np.array_equal(out, w.reshape(-1)) and np.array_equal(conv, wc.reshape(-1))\n"
+        "rc, out, _ = S.process_srcnn(img[:50, :60], 3.0, S.BICUBIC, True, False)\n"
+        "rc2, w2, _ = c.process(img[:50, :60], 3.0, S.BICUBIC, True, False)\n"
+        "assert rc == rc2 == 0 and np.array_equal(out, w2.reshape(-1))\n"
+        "print('OK')\n" % (str(O.ROOT), str(O.ROOT / "tests")))
+    env = dict(__import__("os").environ, SRCNN_B200_DEVICES="0,%d" % (1 % n), SRCNN_B200_MULTI_MIN_ROWS="32")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr

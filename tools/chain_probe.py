@@ -26,7 +26,8 @@ def main():
             rc, got, gconv = ctx.process(img, m, f, True, True)
             assert rc == rc_o == 0
             diff = np.abs(got.reshape(-1).astype(int) - want.astype(int))
-            dc = np.abs(gconv.reshape(-1).astype(int) - wconv.astype(int))
+            assert (gconv is None) == (wconv is None)
+            dc = np.abs(gconv.reshape(-1).astype(int) - wconv.astype(int)) if wconv is not None else np.zeros(1, int)
             print("chain=%-6s %-8s %3dx%-3d d=%d x%.0f f=%d : max|diff| %d LSB (%.4f %% of bytes differ, %.5f %% by > 1), PSNR %.2f dB, conv max %d"
                   % (chain, kind, w, h, d, m, f, diff.max(), 100.0 * (diff > 0).mean(), 100.0 * (diff > 1).mean(),
                      O.psnr(got.reshape(-1), want), dc.max()), flush=True)
