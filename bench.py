@@ -429,6 +429,46 @@ def measure(env, name, steps, warmup, arg_frames=0, want_e2e=True, want_dropin=F
     return res
 
 
+def measure_one_call(ngpu, steps):
+    """ONE host call over all GPUs of the box, single process: srcnn_b200_multi_pass_host on the C3 image (row strips, one per
+    GPU, 6-row halos, no exchange) with pinned host buffers -- the in-library counterpart of the reference spreading one
+    ProcessSRCNN call over all host cores.  Runs on rank 0 BEFORE the process group exists (the other ranks are still waiting
+    in the rendezvous and leave their GPUs idle)."""
+    import libsrcnn_b200 as S
+    import oracle_lib as O
+    h, w, d, m, filt, desc = WORKLOADS["c3"]
+    ow, oh = S.output_dims(w, h, m)
+    img = O.synth("uniform", h, w, d, 43)
+    h_src = S.pinned_empty((h, w, d)); h_src[...] = img
+    h_out = S.pinned_empty((oh, ow, d))
+    res = {"config": config_of("c3", ngpu, 1), "unit": "output MP/s", "scaling": "strong",
+           "api": "srcnn_b200_multi_pass_host (one call, one process, %d GPUs; pinned host buffers)" % ngpu}
+    mg = S.Multi(list(range(ngpu)))
+    try:
+        for _ in range(2):
+            mg.pass_host(h_src, m, filt, False, out=h_out)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            mg.pass_host(h_src, m, filt, False, out=h_out)
+            ts.append(time.perf_counter() - t0)
+        res.update(value=ow * oh / (sum(ts) / len(ts)) / 1e6, ms_per_call=sum(ts) / len(ts) * 1e3, steps=steps,
+                   h2d_bytes_per_step=int(img.nbytes), d2h_bytes_per_step=ow * oh * d)
+        # the same call on ONE GPU of the same handle type, for the ratio
+        m1 = S.Multi([0])
+        m1.pass_host(h_src, m, filt, False, out=h_out)
+        t0 = time.perf_counter()
+        for _ in range(max(2, steps // 2)):
+            m1.pass_host(h_src, m, filt, False, out=h_out)
+        res["value_1gpu"] = ow * oh * max(2, steps // 2) / (time.perf_counter() - t0) / 1e6
+        m1.close()
+    finally:
+        mg.close()
+        for a in (h_src, h_out):
+            S.lib().srcnn_b200_host_free(a.ctypes.data)
+    return res
+
+
 def mem_rooflines(res, hbm):
     return [{"kernel": k, "bytes": int(b), "ms": ms, "gbs": (b / (ms * 1e-3) / 1e9 if ms > 0 else None),
              "frac": (b / (ms * 1e-3) / 1e9 / hbm if ms > 0 else None), "peak_gbs": hbm} for k, b, ms in res["mem_kernels"]]
@@ -451,6 +491,13 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    one_call = None
+    if (int(os.environ.get("WORLD_SIZE", "1")) > 1 and int(os.environ.get("RANK", "0")) == 0 and args.workload == "c2"
+            and args.conv == "tensor" and not args.no_sub):
+        try:
+            one_call = measure_one_call(int(os.environ["WORLD_SIZE"]), min(args.steps, 8))
+        except Exception as e:                                              # noqa: BLE001
+            one_call = {"error": repr(e)}
     env = Env(args.conv)
     name = args.workload
     h, w, d, m, filt, desc = WORKLOADS[name]
@@ -504,6 +551,8 @@ def main():
         "stage_ms": main_res["stage_ms"],
         "cpu_baseline": cpu,
     }
+    if one_call is not None:
+        sub["c3_one_call"] = one_call
     if sub:
         line["sub"] = sub
     emit(line)

@@ -49,6 +49,21 @@ namespace srcnn {
 
 namespace {
 
+/* SRCNN_E1_SPLIT = 1: both epilogue I groups work on EVERY row, each on half of the 64 conv I channels (instead of one group
+ * per row parity on all 64): the D1 -> A2 hand-over of a row takes half as long, which shortens the conv I -> conv II hop that
+ * every row has to pass */
+#ifndef SRCNN_E1_SPLIT
+#define SRCNN_E1_SPLIT 0     /* measured (round 2): 0.1317 ms vs 0.1281 ms */
+#endif
+/* SRCNN_PI = 1 ("producer issues"): there are no dedicated MMA-issuing warps.  The group that writes a layer's A operand
+ * synchronises on a named barrier (bar.sync over its 4 warps) and its first warp issues that layer's MMAs straight away:
+ * im2col -> conv I, epilogue I -> conv II, epilogue II -> conv III.  This removes one mbarrier hand-over (arrive -> wake-up of
+ * a sleeping issuer warp) from every layer of every row -- the pipeline is latency-bound on exactly those hops (the tensor pipe
+ * idles ~28 % of the time while all three issuers wait for operands, profiles/r1_conv_wait_profile.txt). */
+#ifndef SRCNN_PI
+#define SRCNN_PI 0     /* measured (round 2, profiles/r2_conv_variants.txt): 0.2285 ms vs 0.1283 ms -- an issuing lane blocks while the tensor
+                          queue is full, and with it the whole producer group at its next named barrier */
+#endif
 #ifndef SRCNN_E2_DECOUPLE
 #define SRCNN_E2_DECOUPLE 0   /* 1: epilogue II drains both rows of a pair before waiting for the A3 slot (measured: no gain) */
 #endif
@@ -100,6 +115,15 @@ constexpr int SMEM_BYTES = S_TMEM + 16 + 1024;
 static_assert(S_W % 128 == 0 && S_P % 16 == 0 && S_BAR % 8 == 0, "smem layout");
 
 __constant__ float cBias3;
+/* SRCNN_BIAS2_EPI = 1: the conv II bias is added by epilogue II in FP32 (a constant-bank operand of the add: no register, no
+ * load) instead of by a fifth K-step of the conv II GEMM against a constant-1 operand -- one MMA issue and 16 tensor-pipe
+ * clocks less per image row */
+#ifndef SRCNN_BIAS2_EPI
+#define SRCNN_BIAS2_EPI 0     /* measured (round 2): 0.1330 ms vs 0.1283 ms -- the 32 extra adds per row lengthen the conv II -> conv III
+                                 hand-over by more than the K-step they save.  (Re-loading the drained accumulator with the bias
+                                 by tcgen05.st instead: 0.151 ms, the store + its wait sit on the D2 release path.) */
+#endif
+__constant__ float cBias2[32];
 
 /* ---------------------------------------------------------------- PTX helpers */
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -339,8 +363,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     if (tid == 0) {
         for (int i = 0; i < NST; i++) { mbar_init(BAR(Y_FULL + i), 1); mbar_init(BAR(Y_EMPTY + i), 4); }
         for (int b = 0; b < 2; b++) {
-            mbar_init(BAR(A1_FULL + b), SRCNN_MERGE_BAR ? 8 : 4); mbar_init(BAR(M1_DONE + b), 1); mbar_init(BAR(D1_EMPTY_ + b), 4);
-            mbar_init(BAR(A2_FULL + b), SRCNN_MERGE_BAR ? 8 : 4); mbar_init(BAR(M2_DONE + b), 1); mbar_init(BAR(D2_EMPTY_ + b), 4);
+            /* (SRCNN_PI: the operand-written half of the merged barriers is a bar.sync inside the producer group; only the
+             * four drainer warps arrive here) */
+            constexpr int e1w = SRCNN_E1_SPLIT ? 8 : 4;               /* epilogue I warps working on one row */
+            mbar_init(BAR(A1_FULL + b), (SRCNN_MERGE_BAR && !SRCNN_PI) ? 4 + e1w : (SRCNN_PI ? e1w : 4)); mbar_init(BAR(M1_DONE + b), 1);
+            mbar_init(BAR(D1_EMPTY_ + b), e1w);
+            mbar_init(BAR(A2_FULL + b), (SRCNN_MERGE_BAR && !SRCNN_PI) ? e1w + 4 : (SRCNN_PI ? 4 : e1w)); mbar_init(BAR(M2_DONE + b), 1);
+            mbar_init(BAR(D2_EMPTY_ + b), 4);
         }
         for (int j = 0; j < 4; j++) { mbar_init(BAR(A3_FULL + j), 4); mbar_init(BAR(A3_EMPTY + j), 1); }
         for (int b = 0; b < 2; b++) { mbar_init(BAR(M3_DONE + b), 1); mbar_init(BAR(D3_EMPTY + b), 4); }
@@ -385,6 +414,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     __syncwarp();
                 }
             }
+        } else if (SRCNN_PI) {
+            /* (the producer groups issue their own MMAs; these three warps only wait for the end of the kernel) */
         } else if (warp == W_MMA1) {
             /* conv I: the A1 window is a ring of 9 row slots, so the weight image rotates with the row (R = n mod 9) */
             const uint32_t db0 = (uint32_t)umma_desc(sW, 128, (K1 / 8) * 128);
@@ -430,7 +461,8 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                         #pragma unroll
                         for (int s = 0; s < K2 / 16; s++)
                             umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR + 8 * s, db + 16 * s, dh2, umma_idesc(N2), s > 0);
-                        umma_ts(tmem + D2_COL + b * D2_STR, tmem + A1_COL + b * A1_STR + ABIAS_OFF, dbb, dhb, umma_idesc(N2), 1);     /* + bias */
+                        if (!SRCNN_BIAS2_EPI)
+                            umma_ts(tmem + D2_COL + b * D2_STR, tmem + A1_COL + b * A1_STR + ABIAS_OFF, dbb, dhb, umma_idesc(N2), 1);     /* + bias */
                         umma_commit(BAR(M2_DONE + b));
                     }
                     __syncwarp();
@@ -495,6 +527,10 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         reg_inc<96>();
         const int t = (warp - W_IM2COL) * 32 + lane;
         uint32_t it = 0, ck = 0;
+#if SRCNN_PI
+        const uint32_t db1_0 = (uint32_t)umma_desc(sW, 128, (K1 / 8) * 128);
+        constexpr uint32_t dh1 = umma_desc_hi((K1 / 8) * 128);
+#endif
         for (int u = 0; u < span.nunits; u++) {
             const Unit un = unit_of(p, span, u);
             const int hw = ((un.band * kBandCols + 2) & 7) + t;       /* half offset of this lane's window in the box */
@@ -557,7 +593,25 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 }
                 tmem_wait_st();
                 tc_fence_before();
+#if SRCNN_PI
+                asm volatile("bar.sync 3, 128;" ::: "memory");       /* all four lane quarters of A1[b] are written */
+                if (warp == W_IM2COL) {
+                    /* conv I of this row: D1[b] must have been drained by epilogue I (row it-2), then six K-steps against the
+                     * weight image rotated by R = (image row) mod 9 -- a compile-time constant here */
+                    WAITS(1, 1, BAR(D1_EMPTY) + 8u * b, ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t db = db1_0 + (uint32_t)R * (B1_BYTES >> 4);
+                        #pragma unroll
+                        for (int s = 0; s < K1 / 16; s++)
+                            umma_ts(tmem + D1_COL + b * D1_STR, tmem + A1_COL + b * A1_STR + 8 * s, db + 16 * s, dh1, umma_idesc(N1), s > 0);
+                        umma_commit(BAR(M1_DONE) + 8u * b);
+                    }
+                    __syncwarp();
+                }
+#else
                 warp_arrive(BAR(A1_FULL) + 8u * b, lane);
+#endif
                 it++;
             };
             int n = -8;
@@ -573,9 +627,41 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     } else if (warp >= W_E1 && warp < W_E1 + 8) {
         /* ===================== epilogue I (two groups, one per row parity): D1 -> ReLU -> FP16 -> A2 ========== */
         reg_inc<88>();
+#if SRCNN_E1_SPLIT && !SRCNN_PI
+        {
+            const uint32_t half = (uint32_t)(warp - W_E1) >> 2;       /* which 32 of the 64 conv I channels */
+            const int total = total_rows(p, span);
+            if (SRCNN_MERGE_BAR && total > 0) { warp_arrive(BAR(D1_EMPTY + 0), lane); warp_arrive(BAR(D1_EMPTY + 1), lane); }
+            #pragma unroll 1
+            for (int g = 0; g < total; g++) {
+                const uint32_t b = (uint32_t)g & 1u, ph = ((uint32_t)g >> 1) & 1u;
+                const uint32_t d1 = lane_base + D1_COL + b * D1_STR + 32u * half, a2 = lane_base + A2_COL + b * A2_STR + 16u * half;
+                uint32_t v[32];
+                WAITS(3, 0, BAR(M1_DONE) + 8u * b, ph);
+                tc_fence_after();
+                tmem_ld32(d1, v);
+                tmem_wait_ld();
+                tc_fence_before();
+                warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);
+                #pragma unroll
+                for (int m = 0; m < 16; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
+                WAITS(6, 1, BAR(M2_DONE) + 8u * b, ph ^ 1);          /* MMA2 of the previous row of this parity has consumed A2[b] */
+                tc_fence_after();
+                tmem_st16(a2, v);
+                tmem_wait_st();
+                tc_fence_before();
+                warp_arrive(BAR(A2_FULL) + 8u * b, lane);
+            }
+        }
+#else
         const uint32_t b = (uint32_t)(warp - W_E1) >> 2;
         const int total = total_rows(p, span);
         const uint32_t d1 = lane_base + D1_COL + b * D1_STR, a2 = lane_base + A2_COL + b * A2_STR;
+#if SRCNN_PI
+        const uint32_t db2 = (uint32_t)umma_desc(sW + W_B2, 128, (K2 / 8) * 128);
+        const uint32_t dbb2 = (uint32_t)umma_desc(sW + W_B2B, 128, 256);
+        constexpr uint32_t dh2 = umma_desc_hi((K2 / 8) * 128), dhb2 = umma_desc_hi(256);
+#endif
         if (SRCNN_MERGE_BAR && total > 0) warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);     /* D1[b] starts out drained */
         #pragma unroll 1
         for (int g = 0; g < total; g += 2) {
@@ -596,16 +682,42 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             tmem_st16(a2 + 16, v + 16);
             tmem_wait_st();
             tc_fence_before();
+#if SRCNN_PI
+            if (b == 0) asm volatile("bar.sync 4, 128;" ::: "memory"); else asm volatile("bar.sync 5, 128;" ::: "memory");
+            if (((warp - W_E1) & 3) == 0) {
+                /* conv II of this row: D2[b] drained by epilogue II (previous row of this parity), four K-steps */
+                WAITS(5, 1, BAR(D2_EMPTY) + 8u * b, ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    #pragma unroll
+                    for (int s = 0; s < K2 / 16; s++)
+                        umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR + 8 * s, db2 + 16 * s, dh2, umma_idesc(N2), s > 0);
+                    if (!SRCNN_BIAS2_EPI)
+                        umma_ts(tmem + D2_COL + b * D2_STR, tmem + A1_COL + b * A1_STR + ABIAS_OFF, dbb2, dhb2, umma_idesc(N2), 1);
+                    umma_commit(BAR(M2_DONE) + 8u * b);
+                }
+                __syncwarp();
+            }
+#else
             warp_arrive(BAR(A2_FULL) + 8u * b, lane);
+#endif
         }
+#endif
     } else if (warp >= W_E2 && warp < W_E2 + 4) {
         /* ===================== epilogue II: D2 (bias included) -> ReLU -> FP16 -> A3 ring ===================== */
 #if SRCNN_E2_DECOUPLE
         reg_inc<96>();                      /* holds a whole pair (32 + 32 registers); pool: 4096 + 2048 released = 3 x 2048 taken */
+#elif SRCNN_PI
+        /* (keeps its 80 registers: the group also issues conv III) */
 #else
         reg_dec<64>();
 #endif
         uint32_t kg = 0;                                               /* global pair counter */
+#if SRCNN_PI
+        uint32_t sgc = 0;                                              /* global conv III set counter */
+        const uint32_t db3 = (uint32_t)umma_desc(sW + W_B3, 128, 256);
+        constexpr uint32_t dh3 = umma_desc_hi(256);
+#endif
         if (SRCNN_MERGE_BAR && span.nunits > 0) { warp_arrive(BAR(D2_EMPTY + 0), lane); warp_arrive(BAR(D2_EMPTY + 1), lane); }   /* D2 starts out drained */
         for (int u = 0; u < span.nunits; u++) {
             const Unit un = unit_of(p, span, u);
@@ -626,6 +738,10 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     tmem_wait_ld();
                     tc_fence_before();
                     warp_arrive(BAR(D2_EMPTY + b), lane);
+                    if (SRCNN_BIAS2_EPI) {
+                        #pragma unroll
+                        for (int m = 0; m < 32; m++) v[m] = __float_as_uint(__fadd_rn(__uint_as_float(v[m]), cBias2[m]));
+                    }
                     #pragma unroll
                     for (int m = 0; m < 16; m++) h[16 * b + m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
                 }
@@ -643,6 +759,10 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     tmem_wait_ld();
                     tc_fence_before();
                     warp_arrive(BAR(D2_EMPTY + b), lane);
+                    if (SRCNN_BIAS2_EPI == 1) {
+                        #pragma unroll
+                        for (int m = 0; m < 32; m++) v[m] = __float_as_uint(__fadd_rn(__uint_as_float(v[m]), cBias2[m]));
+                    }
                     #pragma unroll
                     for (int m = 0; m < 16; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
                     if (b == 0) {
@@ -654,7 +774,54 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
 #endif
                 tmem_wait_st();
                 tc_fence_before();
+#if SRCNN_PI
+                asm volatile("bar.sync 6, 128;" ::: "memory");       /* the pair is complete in all four lane quarters */
+                if (warp == W_E2 && k >= 2) {
+                    /* conv III, dy on the tensor core: the set of output rows (r0, r0+1), r0 = ra + 2 (k-2), reads the conv II
+                     * pairs k-2, k-1, k of this unit:
+                     *   D3[px][5*o + dx] = sum_{rho<6} sum_ch A3[row clamp(r0-2+rho)][px][ch] * W3[ch][dy = rho-o-2][dx]
+                     * the row clamp of the reference (src/libsrcnn.cpp:461-491) is a choice of ring slot per K-step */
+                    const int pp = k - 2;
+                    const uint32_t kg0 = kg - (uint32_t)k;                 /* pair counter at the start of this unit */
+                    WAITS(9, 1, BAR(D3_EMPTY + (sgc & 1)), ((sgc >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int r0 = un.ra + 2 * pp;
+                        const uint32_t d3 = tmem + D3_COL + (sgc & 1) * D3_STR;
+                        if (r0 >= 2 && r0 + 3 < p.dh) {
+                            const uint32_t kp = kg0 + (uint32_t)pp;
+                            #pragma unroll
+                            for (int j = 0; j < 3; j++) {
+                                const uint32_t pa = tmem + A3_COL + ((kp + j) & 3u) * (2 * A3_SLOT);
+                                #pragma unroll
+                                for (int h = 0; h < 4; h++)
+                                    umma_ts(d3, pa + 8 * h, db3 + (uint32_t)((4 * j + h) * (B3_TILE >> 4)), dh3, umma_idesc(N3), (j | h) > 0);
+                            }
+                        } else {
+                            #pragma unroll
+                            for (int rho = 0; rho < 6; rho++) {
+                                int q = r0 - 2 + rho;
+                                q = q < 0 ? 0 : (q > p.dh - 1 ? p.dh - 1 : q);
+                                const uint32_t slot = (2u * kg0 + (uint32_t)(q - (un.ra - 2))) & 7u;
+                                const uint32_t a = tmem + A3_COL + slot * A3_SLOT;
+                                umma_ts(d3, a,     db3 + (uint32_t)((2 * rho) * (B3_TILE >> 4)),     dh3, umma_idesc(N3), rho > 0);
+                                umma_ts(d3, a + 8, db3 + (uint32_t)((2 * rho + 1) * (B3_TILE >> 4)), dh3, umma_idesc(N3), 1);
+                            }
+                        }
+                        umma_commit(BAR(M3_DONE + (sgc & 1)));
+                        /* pair kg0+pp is dead after this set; the last set of a unit retires the remaining two */
+                        umma_commit(BAR(A3_EMPTY) + 8u * ((kg0 + (uint32_t)pp) & 3));
+                        if (pp == un.npairs - 1) {
+                            umma_commit(BAR(A3_EMPTY) + 8u * ((kg0 + (uint32_t)pp + 1) & 3));
+                            umma_commit(BAR(A3_EMPTY) + 8u * ((kg0 + (uint32_t)pp + 2) & 3));
+                        }
+                    }
+                    __syncwarp();
+                    sgc++;
+                }
+#else
                 warp_arrive(BAR(A3_FULL) + 8u * js, lane);
+#endif
             }
         }
     } else {
@@ -832,6 +999,7 @@ int conv_tc_create(ConvTcState** out)
     cudaError_t e = cudaMalloc(&st->d_wimg, WIMG_BYTES);
     if (e == cudaSuccess) e = cudaMemcpy(st->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(cBias3, &SRCNN_B3, sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(cBias2, SRCNN_B2, sizeof(cBias2));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) {

@@ -17,6 +17,7 @@
 #include <string>
 #include <tuple>
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -160,6 +161,9 @@ struct srcnn_b200_ctx {
     bool fuse_front = true;                   /* one-kernel front end (SRCNN_B200_FUSE=0: the separate kernels)       */
     int keep_planes = 0;                      /* tensor mode: 1 = also write the FP32 interpolated Y and the output-size chroma planes
                                                  (getters; first-generation front end), 2 = the FP32 Y plane only, product route kept */
+    bool stage_in = true;                     /* pageable SOURCE rows go through pinned staging too (SRCNN_B200_STAGE_IN=0: off) */
+    bool stage_all = true;                    /* results <= 96 MB: one staging slot per sub-strip (SRCNN_B200_STAGE_ALL=0: three slots) */
+    bool trace = false;                       /* SRCNN_B200_TRACE=1: host-side timeline of every host pass on stderr */
     bool prep2 = true;                        /* second-generation front end on the x2 hand-over route (SRCNN_B200_PREP2=0: off) */
     bool last_has_y32 = false;
     bool last_has_chroma = true;              /* output-size Cb / Cr / A planes of the last pass exist (getters 1-3)   */
@@ -589,6 +593,9 @@ int srcnn_b200_create(int device, srcnn_b200_ctx** out)
     if (const char* e = getenv("SRCNN_B200_CHROMA_UP")) ctx->chroma_up = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_GROUP")) ctx->group_frames = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_PREP2")) ctx->prep2 = atoi(e) != 0;
+    if (const char* e = getenv("SRCNN_B200_STAGE_IN")) ctx->stage_in = atoi(e) != 0;
+    if (const char* e = getenv("SRCNN_B200_STAGE_ALL")) ctx->stage_all = atoi(e) != 0;
+    if (const char* e = getenv("SRCNN_B200_TRACE")) ctx->trace = atoi(e) != 0;
     {
         unsigned nt = std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2));
         if (const char* e = getenv("SRCNN_B200_COPY_THREADS")) nt = (unsigned)std::max(1, atoi(e));
@@ -748,6 +755,8 @@ int srcnn_b200_sync(srcnn_b200_ctx* ctx)
 }
 void* srcnn_b200_stream(srcnn_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+static inline size_t conv_bytes_of(unsigned rows, unsigned ow, const void* conv) { return conv ? (size_t)rows * ow : 0; }
+
 /* An error in the middle of a host pipeline leaves kernels and asynchronous copies of earlier sub-strips in flight -- to the
  * caller's buffers (which it is about to free) and to the context's staging slots (which the next call reuses).  Drain all
  * three streams before the error is reported, and clear the sticky error state. */
@@ -764,6 +773,7 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
                                uint8_t* out_rows, uint8_t* conv_rows, bool async = false)
 {
     if (!ctx || !src || !out_rows) return SRCNN_B200_EINVAL;
+    const std::chrono::steady_clock::time_point t_entry = std::chrono::steady_clock::now();
     Plan p; int rc = make_plan(w, h, d, multiply, filter, row0, row1, p);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
@@ -780,7 +790,12 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
      * while in flight. */
     const size_t row_bytes = (size_t)p.ow * d;
     const size_t out_bytes = (size_t)(row1 - row0) * row_bytes, conv_bytes = (size_t)(row1 - row0) * p.ow;
-    const size_t strip_bytes = ctx->strip_bytes ? ctx->strip_bytes : (size_t)(host_is_pinned(out_rows) ? 4 : 8) << 20;
+    /* sub-strip size: 4 MB of result; a pageable destination too large to be staged whole (below) uses 8 MB (measured,
+     * tools/e2e_probe.py) */
+    const bool out_pinned = host_is_pinned(out_rows);
+    constexpr size_t kStageAllBytes = (size_t)96 << 20;
+    const bool stage_all = ctx->stage_all && !out_pinned && out_bytes + conv_bytes_of(row1 - row0, p.ow, conv_rows) <= kStageAllBytes;
+    const size_t strip_bytes = ctx->strip_bytes ? ctx->strip_bytes : (size_t)((out_pinned || stage_all) ? 4 : 8) << 20;
     unsigned nstrips = (unsigned)std::min<size_t>((out_bytes + strip_bytes / 2) / strip_bytes, kMaxPipeStrips);
     nstrips = std::max(1u, std::min(nstrips, (row1 - row0) / 64u));
     Plan sp[kMaxPipeStrips];
@@ -811,33 +826,48 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
 
     /* pageable destination: DMA into pinned staging slots, worker threads move the rows on (a cudaMemcpy straight
      * into pageable memory is staged by the driver in small chunks and blocks the pipeline) */
-    const bool stage = !async && ctx->stage_pageable && nstrips > 1 && !host_is_pinned(out_rows);
+    const bool stage = !async && ctx->stage_pageable && nstrips > 1 && !out_pinned;
+    /* results of up to 96 MB are staged whole (one slot per sub-strip): the GPU side of the call is then enqueued in one go
+     * and never waits for the host's copies; larger results cycle through three slots */
+    const unsigned nslots = (stage && stage_all) ? nstrips : kStageSlots;
     size_t slot_bytes = 0;
     if (stage) {
         for (unsigned i = 0; i < nstrips; i++)
             slot_bytes = std::max(slot_bytes, (size_t)(sp[i].r1 - sp[i].r0) * (row_bytes + (conv_rows ? p.ow : 0)));
         slot_bytes = (slot_bytes + 4095) / 4096 * 4096;
-        CK(ctx->pin_out[0].ensure(slot_bytes * kStageSlots));
+        CK(ctx->pin_out[0].ensure(slot_bytes * nslots));
     }
+    /* pageable source: the rows of a sub-strip are copied into pinned memory by the worker threads and uploaded from there
+     * (a cudaMemcpyAsync from pageable memory is staged by the driver, synchronously and at a third of the DMA rate) */
+    const bool stage_in = !async && ctx->stage_pageable && ctx->stage_in && !host_is_pinned(src);
+    if (stage_in) CK(ctx->pin_in[0].ensure((size_t)(S1 - S0) * src_row_bytes));
     /* events of the sub-strip pipeline; an asynchronous call on buffer set 1 uses the second half of the event pool */
     const unsigned ev0 = (unsigned)bs * 3u * kMaxPipeStrips;
     CK(ensure_pipe_events(ctx, 2 * kMaxPipeStrips));
 
     auto drain = [&](unsigned j) -> int {      /* staging slot j % kStageSlots -> caller's rows */
         CK(cudaEventSynchronize(ctx->pipe_ev[ev0 + 3 * j + 2]));
-        const unsigned char* slot = static_cast<unsigned char*>(ctx->pin_out[0].p) + (size_t)(j % kStageSlots) * slot_bytes;
+        const unsigned char* slot = static_cast<unsigned char*>(ctx->pin_out[0].p) + (size_t)(j % nslots) * slot_bytes;
         const size_t ob = (size_t)(sp[j].r1 - sp[j].r0) * row_bytes, off = (size_t)(sp[j].r0 - row0);
         ctx->copier.copy(out_rows + off * row_bytes, slot, ob);
         if (conv_rows) ctx->copier.copy(conv_rows + off * p.ow, slot + ob, (size_t)(sp[j].r1 - sp[j].r0) * p.ow);
         return 0;
     };
 
+    using clk = std::chrono::steady_clock;
+    const clk::time_point t_enq = clk::now();
     unsigned uploaded = S0;
     for (unsigned i = 0; i < nstrips; i++) {
         cudaEvent_t ev_in = ctx->pipe_ev[ev0 + 3 * i], ev_k = ctx->pipe_ev[ev0 + 3 * i + 1], ev_out = ctx->pipe_ev[ev0 + 3 * i + 2];
         if (sp[i].s1 > uploaded) {
-            CK(cudaMemcpyAsync(d_src + (size_t)(uploaded - S0) * src_row_bytes, src + (size_t)uploaded * src_row_bytes,
-                               (size_t)(sp[i].s1 - uploaded) * src_row_bytes, cudaMemcpyHostToDevice, ctx->stream_in));
+            const size_t o = (size_t)(uploaded - S0) * src_row_bytes, n = (size_t)(sp[i].s1 - uploaded) * src_row_bytes;
+            const uint8_t* from = src + (size_t)uploaded * src_row_bytes;
+            if (stage_in) {
+                uint8_t* pin = static_cast<uint8_t*>(ctx->pin_in[0].p) + o;
+                ctx->copier.copy(pin, from, n);
+                from = pin;
+            }
+            CK(cudaMemcpyAsync(d_src + o, from, n, cudaMemcpyHostToDevice, ctx->stream_in));
             uploaded = sp[i].s1;
         }
         CK(cudaEventRecord(ev_in, ctx->stream_in));
@@ -849,8 +879,8 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
         CK(cudaStreamWaitEvent(ctx->stream_out, ev_k, 0));
         const size_t ob = (size_t)(sp[i].r1 - sp[i].r0) * row_bytes, cb = (size_t)(sp[i].r1 - sp[i].r0) * p.ow;
         if (stage) {
-            if (i >= kStageSlots && (rc = drain(i - kStageSlots))) return rc;      /* slot free again */
-            unsigned char* slot = static_cast<unsigned char*>(ctx->pin_out[0].p) + (size_t)(i % kStageSlots) * slot_bytes;
+            if (i >= nslots && (rc = drain(i - nslots))) return rc;      /* slot free again */
+            unsigned char* slot = static_cast<unsigned char*>(ctx->pin_out[0].p) + (size_t)(i % nslots) * slot_bytes;
             CK(cudaMemcpyAsync(slot, d_out + off * row_bytes, ob, cudaMemcpyDeviceToHost, ctx->stream_out));
             if (conv_rows) CK(cudaMemcpyAsync(slot + ob, d_conv + off * p.ow, cb, cudaMemcpyDeviceToHost, ctx->stream_out));
         } else {
@@ -867,10 +897,17 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
         ctx->async_seq++;
         return 0;
     }
+    const clk::time_point t_drain = clk::now();
     if (stage)
-        for (unsigned j = nstrips > kStageSlots ? nstrips - kStageSlots : 0; j < nstrips; j++)
+        for (unsigned j = nstrips > nslots ? nstrips - nslots : 0; j < nstrips; j++)
             if ((rc = drain(j))) return rc;
     CK(cudaStreamSynchronize(ctx->stream_out));
+    if (ctx->trace) {
+        const clk::time_point t_end = clk::now();
+        auto us = [](clk::time_point a, clk::time_point b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() * 1e-3; };
+        fprintf(stderr, "srcnn trace: %u sub-strips, stage_out %d (%u slots) stage_in %d | set-up %.0f us, enqueue %.0f us, drain+tail %.0f us, total %.0f us\n",
+                nstrips, (int)stage, nslots, (int)stage_in, us(t_entry, t_enq), us(t_enq, t_drain), us(t_drain, t_end), us(t_entry, t_end));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     collect_timing(ctx);
     return 0;                                 /* (the plane getters describe the last sub-strip) */
