@@ -96,6 +96,11 @@ int srcnn_b200_strip_geometry(unsigned w, unsigned h, unsigned d, float multiply
 int srcnn_b200_pass_device(srcnn_b200_ctx* ctx, const void* d_src, unsigned w, unsigned h, unsigned d,
                            float multiply, int filter, unsigned row0, unsigned row1,
                            void* d_out, void* d_conv);
+/* CUDA graphs for srcnn_b200_pass_device (default off; SRCNN_B200_GRAPH=1): a pass repeated with the same geometry and the same
+ * pointers is captured on its second call (front end -> fused conv -> colour-out, programmatic-dependent-launch edges included)
+ * and replayed afterwards with a single cudaGraphLaunch.  srcnn_b200_graph_replays counts the replays. */
+int   srcnn_b200_set_graphs(srcnn_b200_ctx* ctx, int on);
+unsigned long long srcnn_b200_graph_replays(const srcnn_b200_ctx* ctx);
 int   srcnn_b200_sync(srcnn_b200_ctx* ctx);
 void* srcnn_b200_stream(srcnn_b200_ctx* ctx);            /* cudaStream_t */
 

@@ -67,6 +67,8 @@ def lib():
         L.srcnn_b200_multi_pass_host.argtypes = [vp, vp, u, u, u, f, i, vp, vp]
         L.srcnn_b200_multi_process_host.argtypes = [vp, vp, u, u, u, f, i, i, vp, vp]
         L.srcnn_b200_multi_batch_host.argtypes = [vp, vp, u, u, u, u, f, i, vp, vp]
+        L.srcnn_b200_set_graphs.argtypes = [vp, i]
+        L.srcnn_b200_graph_replays.argtypes = [vp]; L.srcnn_b200_graph_replays.restype = C.c_ulonglong
         L.srcnn_b200_sync.argtypes = [vp]
         L.srcnn_b200_stream.argtypes = [vp]; L.srcnn_b200_stream.restype = vp
         L.srcnn_b200_process_host.argtypes = [vp, vp, u, u, u, f, i, i, vp, vp]
@@ -238,6 +240,13 @@ class Context:
         r0, r1 = rows if rows is not None else (0, oh)
         self._ck(self.L.srcnn_b200_pass_device(self.h, d_src, w, h, d, multiply, int(filt), r0, r1, d_out,
                                                d_conv or None), "pass_device")
+
+    def set_graphs(self, on=True):
+        self._ck(self.L.srcnn_b200_set_graphs(self.h, int(on)), "set_graphs")
+
+    @property
+    def graph_replays(self):
+        return int(self.L.srcnn_b200_graph_replays(self.h))
 
     def sync(self):
         self._ck(self.L.srcnn_b200_sync(self.h), "sync")

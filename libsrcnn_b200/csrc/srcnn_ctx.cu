@@ -54,7 +54,10 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-/* host-side memcpy spread over a few persistent worker threads (pinned staging -> the caller's pageable rows) */
+/* host-side memcpy spread over a few persistent worker threads (pinned staging <-> the caller's pageable rows), and
+ * first-touch of a fresh result buffer in the background: a buffer that just came from new[] has no pages yet, and the kernel
+ * zeroes every page on its first write -- 0.7 ms for a 25 MB result on one thread (tools/pageable_probe.py), paid here by the
+ * workers while the GPU is still busy with the first sub-strips */
 class HostCopier {
 public:
     ~HostCopier() { stop(); }
@@ -65,6 +68,7 @@ public:
     }
     void stop()
     {
+        wait();
         { std::lock_guard<std::mutex> g(m_); quit_ = true; }
         cv_.notify_all();
         for (auto& t : th_) t.join();
@@ -72,39 +76,60 @@ public:
     }
     void copy(unsigned char* dst, const unsigned char* src, size_t n)
     {
+        wait();                                                                 /* (a background touch may still be running) */
         const size_t parts = th_.size() + 1;
         if (parts == 1 || n < (size_t)256 << 10) { memcpy(dst, src, n); return; }
         const size_t slice = ((n + parts - 1) / parts + 4095) / 4096 * 4096;
-        {
-            std::lock_guard<std::mutex> g(m_);
-            dst_ = dst; src_ = src; n_ = n; slice_ = slice; pending_ = (unsigned)th_.size(); gen_++;
-        }
-        cv_.notify_all();
+        post(dst, src, n, slice, 1);
         memcpy(dst, src, std::min(slice, n));                                   /* the caller takes slice 0 */
+        wait();
+    }
+    /* write one byte into every 4 KB of [dst, dst + n) on the worker threads; returns at once, wait() joins */
+    void touch_async(unsigned char* dst, size_t n)
+    {
+        wait();
+        if (th_.empty() || n < (size_t)1 << 20) return;
+        const size_t slice = ((n + th_.size() - 1) / th_.size() + 4095) / 4096 * 4096;
+        post(dst, nullptr, n, slice, 0);
+    }
+    void wait()
+    {
         std::unique_lock<std::mutex> l(m_);
         done_.wait(l, [this] { return pending_ == 0; });
     }
 private:
+    void post(unsigned char* dst, const unsigned char* src, size_t n, size_t slice, unsigned first)
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            dst_ = dst; src_ = src; n_ = n; slice_ = slice; first_ = first; pending_ = (unsigned)th_.size(); gen_++;
+        }
+        cv_.notify_all();
+    }
     void loop(unsigned id)
     {
         unsigned long seen = 0;
         for (;;) {
-            unsigned char* d; const unsigned char* s; size_t n, sl;
+            unsigned char* d; const unsigned char* s; size_t n, sl; unsigned first;
             {
                 std::unique_lock<std::mutex> l(m_);
                 cv_.wait(l, [&] { return quit_ || gen_ != seen; });
                 if (quit_) return;
-                seen = gen_; d = dst_; s = src_; n = n_; sl = slice_;
+                seen = gen_; d = dst_; s = src_; n = n_; sl = slice_; first = first_;
             }
-            const size_t a = (size_t)(id + 1) * sl;
-            if (a < n) memcpy(d + a, s + a, std::min(sl, n - a));
-            { std::lock_guard<std::mutex> g(m_); if (--pending_ == 0) done_.notify_one(); }
+            const size_t a = (size_t)(id + first) * sl;
+            if (a < n) {
+                const size_t len = std::min(sl, n - a);
+                if (s) memcpy(d + a, s + a, len);
+                else for (size_t o = 0; o < len; o += 4096) static_cast<volatile unsigned char*>(d + a)[o] = 0;
+            }
+            { std::lock_guard<std::mutex> g(m_); if (--pending_ == 0) done_.notify_all(); }
         }
     }
     std::vector<std::thread> th_;
     std::mutex m_; std::condition_variable cv_, done_;
     unsigned char* dst_ = nullptr; const unsigned char* src_ = nullptr; size_t n_ = 0, slice_ = 0;
-    unsigned pending_ = 0; unsigned long gen_ = 0; bool quit_ = false;
+    unsigned pending_ = 0, first_ = 0; unsigned long gen_ = 0; bool quit_ = false;
 };
 
 constexpr unsigned kMaxPipeStrips = 32, kStageSlots = 3;
@@ -157,10 +182,17 @@ struct srcnn_b200_ctx {
                                                  memory, 8 MB into pageable memory (measured, tools/e2e_probe.py); SRCNN_B200_STRIP_MB */
     bool stage_pageable = true;               /* pageable results go through pinned staging (SRCNN_B200_STAGE=0: off) */
     std::vector<cudaEvent_t> pipe_ev;         /* 3 per sub-strip: uploaded, computed, downloaded                      */
-    HostCopier copier;
+    HostCopier copier, toucher;
     bool fuse_front = true;                   /* one-kernel front end (SRCNN_B200_FUSE=0: the separate kernels)       */
     int keep_planes = 0;                      /* tensor mode: 1 = also write the FP32 interpolated Y and the output-size chroma planes
                                                  (getters; first-generation front end), 2 = the FP32 Y plane only, product route kept */
+    /* CUDA graphs (srcnn_b200_set_graphs): a device-resident pass that is repeated with the same geometry and pointers is captured
+     * once (prep -> conv -> colour-out with their programmatic-dependent-launch edges) and replayed with one cudaGraphLaunch */
+    bool graphs = false;
+    struct GraphEntry { std::vector<unsigned long long> key; int seen = 0; cudaGraphExec_t exec = nullptr; };
+    std::vector<GraphEntry> graph_cache;
+    unsigned long long graph_replays = 0;
+    bool prefault = true;                     /* pageable results: first touch by the worker threads while the GPU works (SRCNN_B200_PREFAULT=0) */
     bool stage_in = true;                     /* pageable SOURCE rows go through pinned staging too (SRCNN_B200_STAGE_IN=0: off) */
     bool stage_all = true;                    /* results <= 96 MB: one staging slot per sub-strip (SRCNN_B200_STAGE_ALL=0: three slots) */
     bool trace = false;                       /* SRCNN_B200_TRACE=1: host-side timeline of every host pass on stderr */
@@ -594,12 +626,15 @@ int srcnn_b200_create(int device, srcnn_b200_ctx** out)
     if (const char* e = getenv("SRCNN_B200_GROUP")) ctx->group_frames = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_PREP2")) ctx->prep2 = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_STAGE_IN")) ctx->stage_in = atoi(e) != 0;
+    if (const char* e = getenv("SRCNN_B200_PREFAULT")) ctx->prefault = atoi(e) != 0;
+    if (const char* e = getenv("SRCNN_B200_GRAPH")) ctx->graphs = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_STAGE_ALL")) ctx->stage_all = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_TRACE")) ctx->trace = atoi(e) != 0;
     {
         unsigned nt = std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 2));
         if (const char* e = getenv("SRCNN_B200_COPY_THREADS")) nt = (unsigned)std::max(1, atoi(e));
         ctx->copier.start(nt - 1);
+        ctx->toucher.start(std::min(3u, std::max(1u, nt / 2)));
     }
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking) == cudaSuccess &&
@@ -627,6 +662,7 @@ void srcnn_b200_destroy(srcnn_b200_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& g : ctx->graph_cache) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto& kv : ctx->tables) { cudaFree(kv.second->dev); delete kv.second; }
     if (ctx->tc) conv_tc_destroy(ctx->tc);
     for (int i = 0; i < 2; i++) {
@@ -642,7 +678,7 @@ void srcnn_b200_destroy(srcnn_b200_ctx* ctx)
     ctx->planes_src.release(); ctx->tmp.release(); ctx->planes_dst.release(); ctx->y16.release(); ctx->yprime.release();
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
-    ctx->copier.stop();
+    ctx->copier.stop(); ctx->toucher.stop();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
     if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
@@ -742,9 +778,71 @@ int srcnn_b200_pass_device(srcnn_b200_ctx* ctx, const void* d_src, unsigned w, u
     Plan p; int rc = make_plan(w, h, d, multiply, filter, row0, row1, p);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    return run_pass(ctx, p, static_cast<const uint8_t*>(d_src), 0, static_cast<uint8_t*>(d_out),
-                    static_cast<uint8_t*>(d_conv));
+    const uint8_t* src8 = static_cast<const uint8_t*>(d_src);
+    uint8_t *out8 = static_cast<uint8_t*>(d_out), *conv8 = static_cast<uint8_t*>(d_conv);
+    if (!ctx->graphs || ctx->timing) return run_pass(ctx, p, src8, 0, out8, conv8);
+
+    /* everything the launch sequence depends on: the call's arguments, the mode switches, and the context's scratch buffers
+     * (a grown buffer has a new address: the entry then no longer matches and the pass is captured again) */
+    uint32_t mbits; memcpy(&mbits, &multiply, 4);
+    auto key_now = [&] {
+        return std::vector<unsigned long long>{
+            (unsigned long long)(uintptr_t)d_src, (unsigned long long)(uintptr_t)d_out, (unsigned long long)(uintptr_t)d_conv,
+            ((unsigned long long)w << 32) | h, ((unsigned long long)d << 32) | mbits, ((unsigned long long)row0 << 32) | row1,
+            ((unsigned long long)(unsigned)filter << 32) | ((unsigned)ctx->conv_mode << 8) | ((unsigned)ctx->keep_planes << 4) |
+                ((unsigned)ctx->fuse_front << 3) | ((unsigned)ctx->chroma_up << 2) | ((unsigned)ctx->prep2 << 1) | (unsigned)ctx->fuse_color,
+            (unsigned long long)(uintptr_t)ctx->y16.p, (unsigned long long)(uintptr_t)ctx->yprime.p,
+            (unsigned long long)(uintptr_t)ctx->chroma_src.p, (unsigned long long)(uintptr_t)ctx->planes_dst.p,
+            (unsigned long long)(uintptr_t)ctx->planes_src.p, (unsigned long long)(uintptr_t)ctx->tmp.p };
+    };
+    std::vector<unsigned long long> key = key_now();
+    srcnn_b200_ctx::GraphEntry* e = nullptr;
+    for (auto& g : ctx->graph_cache) if (g.key == key) { e = &g; break; }
+    if (e && e->exec) {
+        CK(cudaGraphLaunch(e->exec, ctx->stream));
+        ctx->graph_replays++; ctx->launches += 3;
+        ctx->last = p; ctx->have_last = true; ctx->last_group = 1;
+        return 0;
+    }
+    if (!e) {
+        /* first sighting: run it plainly (tables are built and uploaded, buffers grow -- none of that may happen inside a capture) */
+        rc = run_pass(ctx, p, src8, 0, out8, conv8);
+        if (rc) return rc;
+        if (ctx->graph_cache.size() >= 16) {                                  /* small cache, oldest entry goes */
+            if (ctx->graph_cache.front().exec) cudaGraphExecDestroy(ctx->graph_cache.front().exec);
+            ctx->graph_cache.erase(ctx->graph_cache.begin());
+        }
+        srcnn_b200_ctx::GraphEntry ne; ne.key = key_now(); ne.seen = 1;       /* (the key AFTER the run: buffers may have grown) */
+        ctx->graph_cache.push_back(ne);
+        return 0;
+    }
+    /* second sighting: capture the launch sequence, instantiate, replay */
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    rc = run_pass(ctx, p, src8, 0, out8, conv8);
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        e->seen = 0; e->key.clear();                                          /* not capturable: never try this entry again */
+        ctx->graphs = false;
+        return rc ? rc : run_pass(ctx, p, src8, 0, out8, conv8);
+    }
+    ce = cudaGraphInstantiate(&e->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { e->exec = nullptr; cudaGetLastError(); ctx->graphs = false; return run_pass(ctx, p, src8, 0, out8, conv8); }
+    CK(cudaGraphLaunch(e->exec, ctx->stream));
+    ctx->graph_replays++;
+    return 0;
 }
+
+int srcnn_b200_set_graphs(srcnn_b200_ctx* ctx, int on)
+{
+    if (!ctx) return SRCNN_B200_EINVAL;
+    ctx->graphs = on != 0;
+    return 0;
+}
+unsigned long long srcnn_b200_graph_replays(const srcnn_b200_ctx* ctx) { return ctx ? ctx->graph_replays : 0; }
 
 int srcnn_b200_sync(srcnn_b200_ctx* ctx)
 {
@@ -762,6 +860,7 @@ static inline size_t conv_bytes_of(unsigned rows, unsigned ow, const void* conv)
  * three streams before the error is reported, and clear the sticky error state. */
 static void drain_streams(srcnn_b200_ctx* ctx)
 {
+    ctx->toucher.wait();
     cudaStreamSynchronize(ctx->stream_in);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->stream_out);
@@ -839,14 +938,16 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
     }
     /* pageable source: the rows of a sub-strip are copied into pinned memory by the worker threads and uploaded from there
      * (a cudaMemcpyAsync from pageable memory is staged by the driver, synchronously and at a third of the DMA rate) */
-    const bool stage_in = !async && ctx->stage_pageable && ctx->stage_in && !host_is_pinned(src);
+    /* (only when the result is staged as well: with a pinned destination the driver's own path is faster, measured) */
+    const bool stage_in = stage && ctx->stage_in && !host_is_pinned(src);
     if (stage_in) CK(ctx->pin_in[0].ensure((size_t)(S1 - S0) * src_row_bytes));
     /* events of the sub-strip pipeline; an asynchronous call on buffer set 1 uses the second half of the event pool */
     const unsigned ev0 = (unsigned)bs * 3u * kMaxPipeStrips;
     CK(ensure_pipe_events(ctx, 2 * kMaxPipeStrips));
 
-    auto drain = [&](unsigned j) -> int {      /* staging slot j % kStageSlots -> caller's rows */
+    auto drain = [&](unsigned j) -> int {      /* staging slot j % nslots -> caller's rows */
         CK(cudaEventSynchronize(ctx->pipe_ev[ev0 + 3 * j + 2]));
+        ctx->toucher.wait();                   /* (the background first touch writes into the same pages) */
         const unsigned char* slot = static_cast<unsigned char*>(ctx->pin_out[0].p) + (size_t)(j % nslots) * slot_bytes;
         const size_t ob = (size_t)(sp[j].r1 - sp[j].r0) * row_bytes, off = (size_t)(sp[j].r0 - row0);
         ctx->copier.copy(out_rows + off * row_bytes, slot, ob);
@@ -856,6 +957,10 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
 
     using clk = std::chrono::steady_clock;
     const clk::time_point t_enq = clk::now();
+    /* a fresh result buffer (ProcessSRCNN hands over new[] memory): first touch in the background, joined by the first copy */
+    if (stage && ctx->prefault) {
+        ctx->toucher.touch_async(out_rows, out_bytes);                 /* (its own threads: the copier stages source rows meanwhile) */
+    }
     unsigned uploaded = S0;
     for (unsigned i = 0; i < nstrips; i++) {
         cudaEvent_t ev_in = ctx->pipe_ev[ev0 + 3 * i], ev_k = ctx->pipe_ev[ev0 + 3 * i + 1], ev_out = ctx->pipe_ev[ev0 + 3 * i + 2];

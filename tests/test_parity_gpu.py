@@ -625,3 +625,39 @@ def test_dropin_over_several_devices():
     env = dict(__import__("os").environ, SRCNN_B200_DEVICES="0,%d" % (1 % n), SRCNN_B200_MULTI_MIN_ROWS="32")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_cuda_graph_replay_equals_plain_launches(ctx):
+    """srcnn_b200_set_graphs: the repeated device-resident pass is captured (second call) and replayed (from the third on); results
+    equal the plain launch sequence, a change of geometry or pointers falls back to a fresh capture"""
+    import torch
+    ctx.set_conv_mode(S.CONV_TENSOR)
+    img = O.synth("uniform", 150, 200, 3, 71)
+    want, wconv = ctx.pass_host(img, 2.0, S.BICUBIC, True)
+    d_src = torch.from_numpy(img).cuda()
+    d_out = torch.zeros((300, 400, 3), dtype=torch.uint8, device="cuda")
+    d_conv = torch.zeros((300, 400), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.set_graphs(True)
+    try:
+        r0 = ctx.graph_replays
+        for i in range(5):
+            d_out.zero_(); d_conv.zero_(); torch.cuda.synchronize()
+            ctx.pass_device(d_src.data_ptr(), 200, 150, 3, 2.0, S.BICUBIC, d_out.data_ptr(), d_conv.data_ptr())
+            ctx.sync()
+            assert np.array_equal(d_out.cpu().numpy(), want) and np.array_equal(d_conv.cpu().numpy(), wconv), "call %d" % i
+        assert ctx.graph_replays - r0 >= 3
+        # another frame through the same pointers: the graph reads the new data
+        img2 = O.synth("uniform", 150, 200, 3, 72)
+        d_src.copy_(torch.from_numpy(img2)); torch.cuda.synchronize()
+        ctx.pass_device(d_src.data_ptr(), 200, 150, 3, 2.0, S.BICUBIC, d_out.data_ptr(), d_conv.data_ptr()); ctx.sync()
+        ctx.set_graphs(False)
+        want2, _ = ctx.pass_host(img2, 2.0, S.BICUBIC, False)
+        assert np.array_equal(d_out.cpu().numpy(), want2)
+        ctx.set_graphs(True)
+        # a strip of the same image (different geometry): its own capture
+        for i in range(3):
+            ctx.pass_device(d_src.data_ptr(), 200, 150, 3, 2.0, S.BICUBIC, d_out[100:].data_ptr(), 0, rows=(100, 300)); ctx.sync()
+            assert np.array_equal(d_out[100:].cpu().numpy(), want2[100:])
+    finally:
+        ctx.set_graphs(False)

@@ -41,7 +41,24 @@ for stage_in, stage_all, mb in (("1", "1", ""), ("0", "1", ""), ("1", "0", ""), 
     ctx.close()
 for k in ("SRCNN_B200_STAGE_IN", "SRCNN_B200_STAGE_ALL", "SRCNN_B200_STRIP_MB"):
     os.environ.pop(k, None)
+# a FRESH pageable result buffer per call (what ProcessSRCNN's new[] is), with and without the background first touch
+for pf in ("1", "0"):
+    os.environ["SRCNN_B200_PREFAULT"] = pf
+    ctx = S.Context(0)
+    def fresh_call():
+        p = libc.malloc(ow * oh * d)
+        buf = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_ubyte)), (oh, ow, d))
+        ctx.pass_host(img, m, f, False, out=buf)
+        libc.free(p)
+    print("prefault=%s  page->FRESH malloc'd buffer %.3f ms" % (pf, t(fresh_call)), flush=True)
+    ctx.close()
+os.environ.pop("SRCNN_B200_PREFAULT", None)
 print("drop-in ProcessSRCNN (defaults) %.3f ms" % t(lambda: S.process_srcnn(img, m, f, False, False, copy=False), 12), flush=True)
+# would keeping freed blocks in the heap help?  (process-wide malloc policy: not something a library should set silently)
+libc.mallopt.argtypes = [C.c_int, C.c_int]
+libc.mallopt(-3, 1 << 30); libc.mallopt(-1, 1 << 30)        # M_MMAP_THRESHOLD, M_TRIM_THRESHOLD
+print("after mallopt(M_MMAP_THRESHOLD / M_TRIM_THRESHOLD = 1 GB): malloc + first touch + free %.3f ms, ProcessSRCNN %.3f ms"
+      % (t(fresh), t(lambda: S.process_srcnn(img, m, f, False, False, copy=False), 12)), flush=True)
 os.environ["SRCNN_B200_TRACE"] = "1"
 c2 = S.Context(0); po = np.empty((oh, ow, d), np.uint8)
 for _ in range(4):
