@@ -480,6 +480,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 #pragma unroll 1
                 for (int pp = 0; pp < un.npairs; pp++, sg++) {
                     const uint32_t kn = kg0 + (uint32_t)pp + 2;           /* newest pair this set reads */
+                    if (pp == 0) {
+                        /* the first set of a unit also reads the unit's first two pairs.  Their completion is implied by the
+                         * newest pair's (same four producer warps, in order), but every completed phase of a barrier gets its own
+                         * wait: no phase is ever skipped (compute-sanitizer synccheck: "missing wait") */
+                        WAITS(8, 0, BAR(A3_FULL) + 8u * (kg0 & 3), (kg0 >> 2) & 1);
+                        WAITS(8, 0, BAR(A3_FULL) + 8u * ((kg0 + 1) & 3), ((kg0 + 1) >> 2) & 1);
+                    }
                     WAITS(8, 0, BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
                     WAITS(9, 1, BAR(D3_EMPTY + (sg & 1)), ((sg >> 1) & 1) ^ 1);
                     tc_fence_after();
