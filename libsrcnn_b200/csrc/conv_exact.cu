@@ -77,15 +77,25 @@ conv_exact_kernel(const float* __restrict__ y, int dw, int dh, int win_row0, int
         float acc2[32];
         #pragma unroll
         for (int n = 0; n < 32; n++) acc2[n] = 0.f;
+        /* four conv I filters at a time: each filter's 81-term sum is a serial chain of dependent adds (the reference's order must
+         * be kept), four independent chains hide the add latency; the conv II sums then take the four results in filter order */
+        constexpr int KB = 4;
         #pragma unroll 1
-        for (int k = 0; k < 64; k++) {
-            float t = 0.f;
+        for (int k = 0; k < 64; k += KB) {
+            float t[KB];
             #pragma unroll
-            for (int tap = 0; tap < 81; tap++) t = __fadd_rn(t, __fmul_rn(cW1[tap][k], win[tap]));
-            t = __fadd_rn(t, cB1[k]);
-            t = (t >= 0.f) ? t : 0.f;
+            for (int j = 0; j < KB; j++) t[j] = 0.f;
             #pragma unroll
-            for (int n = 0; n < 32; n++) acc2[n] = __fadd_rn(acc2[n], __fmul_rn(t, cW2[k][n]));
+            for (int tap = 0; tap < 81; tap++)
+                #pragma unroll
+                for (int j = 0; j < KB; j++) t[j] = __fadd_rn(t[j], __fmul_rn(cW1[tap][k + j], win[tap]));
+            #pragma unroll
+            for (int j = 0; j < KB; j++) {
+                float u = __fadd_rn(t[j], cB1[k + j]);
+                u = (u >= 0.f) ? u : 0.f;
+                #pragma unroll
+                for (int n = 0; n < 32; n++) acc2[n] = __fadd_rn(acc2[n], __fmul_rn(u, cW2[k + j][n]));
+            }
         }
         #pragma unroll
         for (int n = 0; n < 32; n++) {

@@ -49,6 +49,13 @@ namespace srcnn {
 
 namespace {
 
+/* SRCNN_A1_EARLY = 1: the conv I issuer runs its six K-steps in a rotated order -- first the (at most three) K-steps that read
+ * the two oldest window rows, i.e. the ten operand columns im2col overwrites next -- and commits to a second barrier (A1_FREE)
+ * right after them; im2col waits for that barrier instead of for the whole row's MMAs and starts its partial rewrite while the
+ * remaining K-steps are still running.  Needs SRCNN_A1_PARTIAL. */
+#ifndef SRCNN_A1_EARLY
+#define SRCNN_A1_EARLY 0
+#endif
 /* SRCNN_E1_SPLIT = 1: both epilogue I groups work on EVERY row, each on half of the 64 conv I channels (instead of one group
  * per row parity on all 64): the D1 -> A2 hand-over of a row takes half as long, which shortens the conv I -> conv II hop that
  * every row has to pass */
@@ -105,7 +112,8 @@ constexpr int W_TMA = W_CTL, W_MMA1 = W_CTL + 1, W_MMA2 = W_CTL + 2, W_MMA3 = W_
 #endif
 enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + 2, D1_EMPTY_ = M1_DONE + 2,
        A2_FULL = D1_EMPTY_ + 2, M2_DONE = A2_FULL + 2, D2_EMPTY_ = M2_DONE + 2,
-       A3_FULL = D2_EMPTY_ + 2, A3_EMPTY = A3_FULL + 4, M3_DONE = A3_EMPTY + 4, D3_EMPTY = M3_DONE + 2, NBAR = D3_EMPTY + 2,
+       A3_FULL = D2_EMPTY_ + 2, A3_EMPTY = A3_FULL + 4, M3_DONE = A3_EMPTY + 4, D3_EMPTY = M3_DONE + 2, A1_FREE = D3_EMPTY + 2,
+       NBAR = A1_FREE + 2,
        D1_EMPTY = SRCNN_MERGE_BAR ? A1_FULL : D1_EMPTY_, D2_EMPTY = SRCNN_MERGE_BAR ? A2_FULL : D2_EMPTY_ };
 
 /* dynamic shared memory layout (offsets from a 1024-byte aligned base) */
@@ -372,7 +380,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             mbar_init(BAR(D2_EMPTY_ + b), 4);
         }
         for (int j = 0; j < 4; j++) { mbar_init(BAR(A3_FULL + j), 4); mbar_init(BAR(A3_EMPTY + j), 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(BAR(M3_DONE + b), 1); mbar_init(BAR(D3_EMPTY + b), 4); }
+        for (int b = 0; b < 2; b++) { mbar_init(BAR(M3_DONE + b), 1); mbar_init(BAR(D3_EMPTY + b), 4); mbar_init(BAR(A1_FREE + b), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA2) {
@@ -434,9 +442,21 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t db = db0 + R * (B1_BYTES >> 4);
+#if SRCNN_A1_EARLY
+                            /* window rows 0 and 1 of this output row sit in ring slots R and R+1 (mod 9), columns 5R .. 5R+9
+                             * (mod 45) = K-steps s0 .. s0+2 (mod 6) with s0 = floor(5R / 8): 0 0 1 1 2 3 3 4 5 for R = 0 .. 8 */
+                            uint32_t s = (uint32_t)((0x543321100ull >> (4 * R)) & 7u);
+                            #pragma unroll
+                            for (int i = 0; i < K1 / 16; i++) {
+                                umma_ts(tmem + D1_COL + b * D1_STR, tmem + A1_COL + b * A1_STR + 8 * s, db + 16 * s, dh1, umma_idesc(N1), i > 0);
+                                if (i == (R == 3 ? 2 : 1)) umma_commit(BAR(A1_FREE + b));      /* (only R = 3 straddles three K-steps) */
+                                s = (s == K1 / 16 - 1) ? 0 : s + 1;
+                            }
+#else
                             #pragma unroll
                             for (int s = 0; s < K1 / 16; s++)
                                 umma_ts(tmem + D1_COL + b * D1_STR, tmem + A1_COL + b * A1_STR + 8 * s, db + 16 * s, dh1, umma_idesc(N1), s > 0);
+#endif
                             umma_commit(BAR(M1_DONE + b));
                         }
                         __syncwarp();
@@ -565,7 +585,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 fetch(n + 8, W[(R + 8) % 9]);
                 if (n < 0) return;
                 const uint32_t b = it & 1, ph = (it >> 1) & 1;
+#if SRCNN_A1_EARLY && SRCNN_A1_PARTIAL && !SRCNN_PI
+                /* partial rewrite: only the K-steps that read the two oldest window rows of row it-2 must have run */
+                WAITS(2, 1, BAR(A1_FREE) + 8u * b, ph ^ 1);
+                if (n < 2) WAITS(2, 1, BAR(M1_DONE) + 8u * b, ph ^ 1);     /* whole operand rewritten: all of row it-2's MMAs */
+#else
                 WAITS(2, 1, BAR(M1_DONE) + 8u * b, ph ^ 1);         /* MMA1 of row it-2 has consumed A1[b] */
+#endif
                 tc_fence_after();
                 const uint32_t dst = lane_base + A1_COL + b * A1_STR;
                 if (!SRCNN_A1_PARTIAL || n < 2) {

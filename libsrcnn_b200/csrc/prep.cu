@@ -411,6 +411,10 @@ __device__ __forceinline__ float byte_f32(uint32_t v)
 }
 
 /* two adjacent pixels: the raw words (requested early) and their channels as floats */
+/* resident CTAs per SM the compiler plans for (register budget 65536 / (256 x this)) */
+#ifndef SRCNN_PREP2_MINB
+#define SRCNN_PREP2_MINB 4
+#endif
 template <int D>
 __device__ __forceinline__ void load_raw2(const uint8_t* __restrict__ p, uint32_t (&r)[3])
 {
@@ -442,7 +446,7 @@ __device__ __forceinline__ double widen(float f)
 }
 
 template <int D, int WY, int SC, bool FMA>
-__global__ void __launch_bounds__(NT, 4)
+__global__ void __launch_bounds__(NT, SRCNN_PREP2_MINB)
 prep2_kernel(const PrepParams p)
 {
     pdl_launch_dependents();                          /* the conv kernel may set itself up while this grid drains */

@@ -9,7 +9,6 @@ and again with each rank (and its pinned buffers, first-touched after the move) 
 box exposes one.  The aggregate download rate x 1 / 24.9 MB is the ceiling of the multi-GPU end-to-end frame rate."""
 import os
 import re
-import subprocess
 import time
 
 import torch
@@ -19,20 +18,14 @@ D2H, H2D, K = 24883200, 6220800, 40
 
 
 def numa_of_gpu(local):
+    """(PCI address, NUMA node or None) of CUDA device `local` (honours CUDA_VISIBLE_DEVICES through torch)"""
     try:
-        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
     except Exception:                                               # noqa: BLE001
-        bdf = None
-    if bdf is None:
-        try:
-            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
-                                 capture_output=True, text=True, timeout=20).stdout.strip()
-            bdf = out.lower().replace("00000000:", "0000:")
-        except Exception:                                           # noqa: BLE001
-            return None, None
-    p = "/sys/bus/pci/devices/%s/numa_node" % bdf.lower()
+        return None, None
     try:
-        node = int(open(p).read())
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
     except Exception:                                               # noqa: BLE001
         return bdf, None
     return bdf, node
