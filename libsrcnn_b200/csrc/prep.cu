@@ -413,7 +413,7 @@ __device__ __forceinline__ float byte_f32(uint32_t v)
 /* two adjacent pixels: the raw words (requested early) and their channels as floats */
 /* resident CTAs per SM the compiler plans for (register budget 65536 / (256 x this)) */
 #ifndef SRCNN_PREP2_MINB
-#define SRCNN_PREP2_MINB 4
+#define SRCNN_PREP2_MINB 5      /* measured: 4 -> 5 CTAs per SM (48 registers, 16-44 bytes spilled): C2 42.1 -> 41.8 us, C3 468 -> 449 us; 6: worse */
 #endif
 template <int D>
 __device__ __forceinline__ void load_raw2(const uint8_t* __restrict__ p, uint32_t (&r)[3])
