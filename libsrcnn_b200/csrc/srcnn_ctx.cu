@@ -207,6 +207,7 @@ struct srcnn_b200_ctx {
     struct GraphEntry { std::vector<unsigned long long> key; int seen = 0; cudaGraphExec_t exec = nullptr; };
     std::vector<GraphEntry> graph_cache;
     unsigned long long graph_replays = 0;
+    bool ramp = true;                         /* host pipeline: small first sub-strips (SRCNN_B200_RAMP=0: uniform cuts) */
     bool prefault = true;                     /* pageable results: first touch by the worker threads while the GPU works (SRCNN_B200_PREFAULT=0) */
     bool stage_in = true;                     /* pageable SOURCE rows go through pinned staging too (SRCNN_B200_STAGE_IN=0: off) */
     bool stage_all = true;                    /* results <= 96 MB: one staging slot per sub-strip (SRCNN_B200_STAGE_ALL=0: three slots) */
@@ -643,6 +644,7 @@ int srcnn_b200_create(int device, srcnn_b200_ctx** out)
     if (const char* e = getenv("SRCNN_B200_STAGE_IN")) ctx->stage_in = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_PREFAULT")) ctx->prefault = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_GRAPH")) ctx->graphs = atoi(e) != 0;
+    if (const char* e = getenv("SRCNN_B200_RAMP")) ctx->ramp = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_STAGE_ALL")) ctx->stage_all = atoi(e) != 0;
     if (const char* e = getenv("SRCNN_B200_TRACE")) ctx->trace = atoi(e) != 0;
     {
@@ -912,10 +914,20 @@ static int pass_host_rows_impl(srcnn_b200_ctx* ctx, const uint8_t* src, unsigned
     const size_t strip_bytes = ctx->strip_bytes ? ctx->strip_bytes : (size_t)((out_pinned || stage_all) ? 4 : 8) << 20;
     unsigned nstrips = (unsigned)std::min<size_t>((out_bytes + strip_bytes / 2) / strip_bytes, kMaxPipeStrips);
     nstrips = std::max(1u, std::min(nstrips, (row1 - row0) / 64u));
+    /* ramp: the first two sub-strips are a quarter and a half of the others, so the first download -- the transfers are what
+     * bounds the call -- starts after ~1 MB of work instead of ~4 MB (cuts are free: every sub-strip is an ordinary row strip) */
+    const bool ramp = ctx->ramp && nstrips >= 3 && nstrips < kMaxPipeStrips && (row1 - row0) / (nstrips + 1) >= 256u;
+    if (ramp) nstrips++;
+    auto cut = [&](unsigned i) -> unsigned {                       /* first row of sub-strip i (i == nstrips: the end) */
+        if (!ramp) return row0 + (unsigned)((size_t)(row1 - row0) * i / nstrips);
+        const double total = (double)nstrips - 1.25;               /* weights 0.25, 0.5, 1, 1, ... */
+        const double upto = i == 0 ? 0.0 : i == 1 ? 0.25 : 0.75 + (double)(i - 2);
+        const unsigned r = row0 + (unsigned)((double)(row1 - row0) * (upto / total) + 0.5);
+        return i >= nstrips ? row1 : std::min(r, row1);
+    };
     Plan sp[kMaxPipeStrips];
     for (unsigned i = 0; i < nstrips; i++) {
-        const unsigned a = row0 + (unsigned)((size_t)(row1 - row0) * i / nstrips);
-        const unsigned b = row0 + (unsigned)((size_t)(row1 - row0) * (i + 1) / nstrips);
+        const unsigned a = cut(i), b = cut(i + 1);
         if ((rc = make_plan(w, h, d, multiply, filter, a, b, sp[i]))) return rc;
         if (p.need_v) source_rows(vy->host, vc->host, sp[i].e0, sp[i].e1, sp[i].s0, sp[i].s1);
         else { sp[i].s0 = sp[i].e0; sp[i].s1 = sp[i].e1; }
