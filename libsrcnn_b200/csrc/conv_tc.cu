@@ -49,6 +49,25 @@ namespace srcnn {
 
 namespace {
 
+#ifndef SRCNN_TMEM0
+#define SRCNN_TMEM0 0     /* measured by reading the SASS: the immediates land in vector registers first and need MORE R2UR, not fewer */
+#endif
+/* SRCNN_ELECT_OUTER = 1: an issuer warp elects its lane ONCE, around its whole row loop, instead of once per row: the per-row
+ * ELECT / BSSY / BSYNC / BRA.DIV / WARPSYNC scaffolding (~9 of ~42 instructions per row) disappears from the single-lane issue
+ * loops, which pace the pipeline (three issuers x ~45 serial instructions per image row at ~10 clk each = the 455 clk row period) */
+#ifndef SRCNN_ELECT_OUTER
+#define SRCNN_ELECT_OUTER 0     /* measured (round 2): 0.1320 ms vs 0.1280 ms -- 33 instead of 42 instructions per row in the issue loops, and slower */
+#endif
+#if SRCNN_ELECT_OUTER
+#define ISSUER_BEGIN if (elect_one()) {
+#define ISSUE_LANE() true
+#define ISSUE_SYNC() ((void)0)
+#else
+#define ISSUER_BEGIN {
+#define ISSUE_LANE() elect_one()
+#define ISSUE_SYNC() __syncwarp()
+#endif
+#define ISSUER_END }
 /* SRCNN_A1_EARLY = 1: the conv I issuer runs its six K-steps in a rotated order -- first the (at most three) K-steps that read
  * the two oldest window rows, i.e. the ten operand columns im2col overwrites next -- and commits to a second barrier (A1_FREE)
  * right after them; im2col waits for that barrier instead of for the whole row's MMAs and starts its partial rewrite while the
@@ -397,7 +416,16 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
      * kernel be scheduled as soon as CTAs of this grid retire */
     pdl_wait();
     pdl_launch_dependents();
+#if SRCNN_TMEM0
+    /* The CTA allocates all 512 columns and is alone on its SM (144 KB of shared memory), so the allocation starts at column 0,
+     * lane 0: address 0.  With the base a compile-time constant every TMEM address of the issuing lanes is an immediate -- the
+     * compiler materialises them in uniform registers directly instead of moving them over from vector registers (R2UR) before
+     * every tcgen05.mma: the single-lane issue loops, ~45 serial instructions per image row each, are the pipeline's pacemakers */
+    if (*reinterpret_cast<volatile uint32_t*>(sgen + S_TMEM) != 0u) __trap();
+    constexpr uint32_t tmem = 0u;
+#else
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + S_TMEM);
+#endif
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);     /* this warp's TMEM lane quarter */
     const Span span = span_of(p);
 
@@ -425,6 +453,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         } else if (SRCNN_PI) {
             /* (the producer groups issue their own MMAs; these three warps only wait for the end of the kernel) */
         } else if (warp == W_MMA1) {
+            ISSUER_BEGIN
             /* conv I: the A1 window is a ring of 9 row slots, so the weight image rotates with the row (R = n mod 9) */
             const uint32_t db0 = (uint32_t)umma_desc(sW, 128, (K1 / 8) * 128);
             constexpr uint32_t dh1 = umma_desc_hi((K1 / 8) * 128);
@@ -440,7 +469,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                         WAITS(0, 0, BAR(A1_FULL + b), ph);
                         if (!SRCNN_MERGE_BAR) WAITS(1, 1, BAR(D1_EMPTY + b), ph ^ 1);
                         tc_fence_after();
-                        if (elect_one()) {
+                        if (ISSUE_LANE()) {
                             const uint32_t db = db0 + R * (B1_BYTES >> 4);
 #if SRCNN_A1_EARLY
                             /* window rows 0 and 1 of this output row sit in ring slots R and R+1 (mod 9), columns 5R .. 5R+9
@@ -459,12 +488,14 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
 #endif
                             umma_commit(BAR(M1_DONE + b));
                         }
-                        __syncwarp();
+                        ISSUE_SYNC();
                         R = (R == NROT - 1) ? 0 : R + 1;
                     }
                 }
             }
+            ISSUER_END
         } else if (warp == W_MMA2) {
+            ISSUER_BEGIN
             const uint32_t db = (uint32_t)umma_desc(sW + W_B2, 128, (K2 / 8) * 128);
             const uint32_t dbb = (uint32_t)umma_desc(sW + W_B2B, 128, 256);
             constexpr uint32_t dh2 = umma_desc_hi((K2 / 8) * 128), dhb = umma_desc_hi(256);
@@ -477,7 +508,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     WAITS(4, 0, BAR(A2_FULL + b), ph);
                     if (!SRCNN_MERGE_BAR) WAITS(5, 1, BAR(D2_EMPTY + b), ph ^ 1);
                     tc_fence_after();
-                    if (elect_one()) {
+                    if (ISSUE_LANE()) {
                         #pragma unroll
                         for (int s = 0; s < K2 / 16; s++)
                             umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR + 8 * s, db + 16 * s, dh2, umma_idesc(N2), s > 0);
@@ -485,10 +516,12 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                             umma_ts(tmem + D2_COL + b * D2_STR, tmem + A1_COL + b * A1_STR + ABIAS_OFF, dbb, dhb, umma_idesc(N2), 1);     /* + bias */
                         umma_commit(BAR(M2_DONE + b));
                     }
-                    __syncwarp();
+                    ISSUE_SYNC();
                 }
             }
+            ISSUER_END
         } else {
+            ISSUER_BEGIN
             /* conv III, dy on the tensor core: one set per pair of output rows (r0, r0+1):
              *   D3[px][5*o + dx] = sum_{rho<6} sum_ch A3[row clamp(r0-2+rho)][px][ch] * W3[ch][dy = rho-o-2][dx]
              * the row clamp of the reference (src/libsrcnn.cpp:461-491) is a choice of ring slot per K-step */
@@ -510,7 +543,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     WAITS(8, 0, BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
                     WAITS(9, 1, BAR(D3_EMPTY + (sg & 1)), ((sg >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    if (elect_one()) {
+                    if (ISSUE_LANE()) {
                         const int r0 = un.ra + 2 * pp;
                         const uint32_t d3 = tmem + D3_COL + (sg & 1) * D3_STR;
                         if (r0 >= 2 && r0 + 3 < p.dh) {
@@ -544,10 +577,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                             umma_commit(BAR(A3_EMPTY) + 8u * ((kg0 + (uint32_t)pp + 2) & 3));
                         }
                     }
-                    __syncwarp();
+                    ISSUE_SYNC();
                 }
                 kg0 += (uint32_t)un.npairs + 2;
             }
+            ISSUER_END
         }
     } else if (warp >= W_IM2COL && warp < W_IM2COL + 4) {
         /* ===================== im2col: smem Y16 ring -> 9-slot register ring -> A1 in TMEM ==================== */
