@@ -227,7 +227,7 @@ bool decode(const unsigned char* data, size_t n, Image& img, std::string& err)
             case T_PNG: return decode_png(data, n, img, err);
             case T_BMP: return decode_bmp(data, n, img, err);
             case T_PNM: return decode_pnm(data, n, img, err);
-            case T_JPEG: err = "JPEG decoding is not built in; convert the file to PNG first"; return false;
+            case T_JPEG: return decode_jpeg(data, n, img, err);
             default: err = "unknown image format"; return false;
         }
     } catch (const std::exception& e) {          /* std::bad_alloc / length_error on absurd dimensions */

@@ -3,7 +3,8 @@
  * The reference CLI (src/test.cpp:134-178, 180-274, 545-590) loads JPEG / PNG / BMP through FLTK + fl_imgtk and writes
  * PNG through libpng; none of those libraries is part of the library proper.  Here: PNG (8/16-bit, all colour types,
  * non-interlaced) decoded and encoded directly on zlib, uncompressed 24/32-bit BMP, and binary PNM (P5/P6).
- * JPEG is not decoded (convert first).  Pure host code, no CUDA.
+ * Baseline JPEG (sequential Huffman, 8-bit, gray / YCbCr, the reference's Pictures/castle.jpg) is decoded by jpegdec.cpp;
+ * progressive files are refused with a message.  Pure host code, no CUDA.
  */
 #ifndef SRCNN_IMGIO_H
 #define SRCNN_IMGIO_H
@@ -27,6 +28,7 @@ bool read_file(const std::string& path, std::vector<unsigned char>& out);
 /* decode; on failure returns false and fills `err` */
 bool decode(const unsigned char* data, size_t n, Image& img, std::string& err);
 bool load(const std::string& path, Image& img, Type* type, std::string& err);
+bool decode_jpeg(const unsigned char* data, size_t n, Image& img, std::string& err);     /* jpegdec.cpp */
 
 /* 8-bit PNG, colour type from d (1 gray, 3 RGB, 4 RGBA), no interlace -- what the reference's savetopng writes */
 bool encode_png(const unsigned char* px, unsigned w, unsigned h, unsigned d, std::vector<unsigned char>& out);

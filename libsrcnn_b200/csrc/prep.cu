@@ -412,6 +412,9 @@ __device__ __forceinline__ float byte_f32(uint32_t v)
 
 /* two adjacent pixels: the raw words (requested early) and their channels as floats */
 /* resident CTAs per SM the compiler plans for (register budget 65536 / (256 x this)) */
+#ifndef SRCNN_PREP2_STOP
+#define SRCNN_PREP2_STOP 0      /* development: 1 / 2 = leave the kernel after colour-in / after the vertical pass (phase timing) */
+#endif
 #ifndef SRCNN_PREP2_MINB
 #define SRCNN_PREP2_MINB 5      /* measured: 4 -> 5 CTAs per SM (48 registers, 16-44 bytes spilled): C2 42.1 -> 41.8 us, C3 468 -> 449 us; 6: worse */
 #endif
@@ -561,6 +564,9 @@ prep2_kernel(const PrepParams p)
     }
     __syncthreads();
 
+#if SRCNN_PREP2_STOP == 1
+    return;                                           /* (timing experiment: colour-in only) */
+#endif
     /* ---- 2. vertical pass, shared -> shared (reference verticalFilter, src/frawscale.cpp:335-385): thread = column pair x row lane */
     {
         const int cp = tid % NCP, rl = tid / NCP;
@@ -589,6 +595,9 @@ prep2_kernel(const PrepParams p)
     }
     __syncthreads();
 
+#if SRCNN_PREP2_STOP == 2
+    return;                                           /* (timing experiment: colour-in + vertical pass) */
+#endif
     /* ---- 3. horizontal pass, shared -> registers -> global (reference horizontalFilter, src/frawscale.cpp:288-332) */
     const int ybase = (int)gy0 - p.strip_row0 + kHaloRows;       /* conv-input plane row of tile row 0 */
     if (col_ok) {

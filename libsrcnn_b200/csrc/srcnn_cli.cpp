@@ -113,7 +113,7 @@ int main(int argc, char** argv)
     printf("\n");
     if (!ok) { printf("- Failed to load image. (%s)\n", err.c_str()); return 1; }
     printf("- Image loaded type : %s | %u x %u x %u bytes\n",
-           type == imgio::T_PNG ? "PNG" : type == imgio::T_BMP ? "BMP" : type == imgio::T_PNM ? "PNM" : "?", img.w, img.h, img.d);
+           type == imgio::T_JPEG ? "JPEG" : type == imgio::T_PNG ? "PNG" : type == imgio::T_BMP ? "BMP" : type == imgio::T_PNM ? "PNM" : "?", img.w, img.h, img.d);
     imgio::to_rgb_or_rgba(img);                                    /* gray -> RGB, as src/test.cpp:44-119 */
     if (img.d < 3) { printf("- Error: Unsupported image.\n"); return 1; }
     if (o.decode_only) {

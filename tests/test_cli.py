@@ -95,14 +95,40 @@ def test_bmp_and_pnm_decode(tmp_path, fmt, d):
     assert np.array_equal(np.asarray(Image.open(tmp_path / "o.png")), want)
 
 
-def test_rejects_garbage_and_jpeg(tmp_path):
+def test_rejects_garbage_and_progressive_jpeg(tmp_path):
     _need_cli()
     (tmp_path / "x.png").write_bytes(b"not an image at all")
     assert _run(CLI, tmp_path / "x.png", "--decode-only").returncode != 0
-    Image.fromarray(_rng_img(8, 8, 3)).save(tmp_path / "x.jpg")
+    Image.fromarray(_rng_img(8, 8, 3)).save(tmp_path / "x.jpg", progressive=True)
     r = _run(CLI, tmp_path / "x.jpg", "--decode-only")
-    assert r.returncode != 0 and "JPEG" in r.stdout
+    assert r.returncode != 0 and "progressive" in r.stdout                   # baseline only: refused with a message
+    (tmp_path / "t.jpg").write_bytes((tmp_path / "x.jpg").read_bytes()[:60])
+    assert _run(CLI, tmp_path / "t.jpg", "--decode-only").returncode != 0    # truncated
     assert _run(CLI).returncode != 0                                         # no arguments: usage, non-zero
+
+
+@pytest.mark.parametrize("name,kw", [("444", dict(subsampling=0)), ("422", dict(subsampling=1)), ("420", dict(subsampling=2)),
+                                     ("q30", dict(subsampling=2, quality=30)), ("gray", None), ("odd", dict(subsampling=2))])
+def test_baseline_jpeg_decode_matches_a_libjpeg_loader(tmp_path, name, kw):
+    """the reference CLI loads JPEG through FLTK / libjpeg (src/test.cpp:145-148, 563-566; its sample Pictures/castle.jpg is a
+    baseline 4:2:0 file): the built-in baseline decoder (jpegdec.cpp: libjpeg's fancy upsampling and colour tables, a plain
+    double-precision IDCT) must stay within 3 LSB of PIL's libjpeg result, with a mean difference below 0.1 LSB"""
+    _need_cli()
+    h, w = (77, 101) if name != "odd" else (33, 47)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([127 + 100 * np.sin(xx / 9.0 + yy / 17.0), 127 + 100 * np.cos(xx / 5.0), 60 + yy * 2.0], 2).clip(0, 255).astype(np.uint8)
+    f = tmp_path / ("t_%s.jpg" % name)
+    if kw is None:
+        Image.fromarray(img[..., 0]).save(f, quality=90)
+    else:
+        Image.fromarray(img).save(f, quality=kw.get("quality", 92), subsampling=kw["subsampling"])
+    r = _run(CLI, f, "--decode-only", tmp_path / "o.png")
+    assert r.returncode == 0 and "JPEG" in r.stdout, r.stdout
+    got = np.asarray(Image.open(tmp_path / "o.png")).astype(int)
+    want = np.asarray(Image.open(f).convert("RGB")).astype(int)
+    assert got.shape == want.shape
+    diff = np.abs(got - want)
+    assert diff.max() <= 3 and diff.mean() < 0.1, (diff.max(), diff.mean())
 
 
 def test_corrupt_and_truncated_png_are_rejected_cleanly(tmp_path):
