@@ -44,6 +44,7 @@ struct AxisTableDev {
     const int*    cleft;
     const double* cw;
     int           cwin;
+    const double* cwt;      /* compact weights transposed: [cwin][dst] (16-byte aligned; NULL without the compact form) */
     int           exact29;  /* all weights have <= 29 significant bits: fma == mul, add */
     int           pow2pair; /* cwin == 2, both weights exact in FP32, one of each pair 0 or a power of two (prep.cu) */
     const void*   pack2;    /* pow2pair only: [dst] int4 { left + idx(tap A), bits(wA), bits(wB), left + idx(tap B) } (color.cu) */

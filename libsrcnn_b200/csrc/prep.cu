@@ -56,6 +56,7 @@ struct PrepParams {
     __half* y16; int pitch, y16_rows; int strip_row0;
     const int *vyl, *vcl, *hyl, *hcl;     /* compact lefts   */
     const double *vyw, *vcw, *hyw, *hcw;  /* compact weights */
+    const double* hywt;                   /* horizontal Y weights transposed [tap][ow] (prep2_kernel) */
     int SR, SC;                 /* shared-memory capacity of the source footprint (rows, columns) */
     /* chroma hand-over at SOURCE resolution (chroma mode 2 only, may be NULL): instead of resampling Cb / Cr / A here, the
      * colour-converted FP32 samples of the footprint are written to csrc[plane][(row - src_row0) * w + col] and the x2
@@ -547,13 +548,17 @@ prep2_kernel(const PrepParams p)
     int o[WY + 1];
     if (col_ok) {
         const int la = __ldg(p.hyl + gx), lb = __ldg(p.hyl + gx + 1);     /* lb - la is 0 or 1 (checked on the host) */
-        #pragma unroll
-        for (int i = 0; i < WY; i++) wa[i] = __ldg(p.hyw + (size_t)gx * WY + i);
-        /* the second column reads the same WY + 1 samples with its weights shifted by lb - la (a zero weight on the sample it
-         * does not use: fma(0, v, acc) == acc for the finite v of an initialised footprint) */
+        /* one 16-byte load per tap brings the weights of both columns: the table is stored tap-major for this (a warp then reads
+         * 512 contiguous bytes per tap; with the destination-major table every lane's 64-byte-strided loads cost a wavefront
+         * each -- a third of all LSU wavefronts of the kernel, and the LSU data pipe is its busiest unit, ncu round 2) */
         double t[WY];
         #pragma unroll
-        for (int i = 0; i < WY; i++) t[i] = __ldg(p.hyw + (size_t)(gx + 1) * WY + i);
+        for (int i = 0; i < WY; i++) {
+            const double2 w2 = __ldg(reinterpret_cast<const double2*>(p.hywt + (size_t)i * p.ow + gx));
+            wa[i] = w2.x; t[i] = w2.y;
+        }
+        /* the second column reads the same WY + 1 samples with its weights shifted by lb - la (a zero weight on the sample it
+         * does not use: fma(0, v, acc) == acc for the finite v of an initialised footprint) */
         const bool sh = lb != la;
         wb[0] = sh ? 0.0 : t[0];
         #pragma unroll
@@ -829,6 +834,8 @@ int launch_prep2(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, 
     p.y16 = y16; p.pitch = g.pitch; p.y16_rows = g.rows; p.strip_row0 = (int)strip_row0;
     p.vyl = vy.cleft; p.vcl = vc.cleft; p.hyl = hy.cleft; p.hcl = hc.cleft;
     p.vyw = vy.cw; p.vcw = vc.cw; p.hyw = hy.cw; p.hcw = hc.cw;
+    p.hywt = hy.cwt;
+    if (!p.hywt) return 0;
     p.SR = max_footprint(h_vyl, vy.cwin, h_vcl, vc.cwin, e0, e1, TH);
     p.SC = max_footprint_even(h_hyl, hy.cwin, h_hcl, hc.cwin, 0, ow, TW);
     if (p.SC > 72 || p.SR > 28) return 0;                       /* prep2_kernel: SC = 72, at most 4 x 7 footprint rows */
@@ -851,7 +858,7 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
 {
     if (nframes > 1 && (planes || write_y32 || !csrc)) return 0;     /* groups: the x2 hand-over route only */
     if (!prep_supported(vy, vc, hy, hc) || (d != 3 && d != 4)) return 0;
-    PrepParams p;
+    PrepParams p{};
     p.src = src; p.w = w; p.src_row0 = src_row0; p.ow = ow; p.oh = oh; p.e0 = e0; p.e1 = e1;
     p.planes = planes; p.plane_stride = plane_stride; p.write_y32 = write_y32 ? 1 : 0;
     p.y16 = y16; p.pitch = g.pitch; p.y16_rows = g.rows; p.strip_row0 = (int)strip_row0;

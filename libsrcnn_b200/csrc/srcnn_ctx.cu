@@ -269,7 +269,10 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     const size_t wbytes = h.w.size() * sizeof(double), cbytes = h.cw.size() * sizeof(double);
     const size_t pbytes = (h.compact && h.pow2pair) ? (size_t)dst * 16 : 0;       /* pack2 (color.cu) */
     const size_t poff = (ints_al + 2 * wbytes + cbytes + 15) / 16 * 16;
-    const size_t bytes = poff + pbytes;
+    /* cwt: the compact weights transposed, [tap][dst] -- adjacent destination samples are adjacent in memory, so a warp reading
+     * one tap of its 64 columns touches 512 contiguous bytes instead of 32 scattered 64-byte-strided words (prep.cu: prep2_kernel) */
+    const size_t toff = (poff + pbytes + 15) / 16 * 16, tbytes = h.compact ? cbytes : 0;
+    const size_t bytes = toff + tbytes;
     std::vector<unsigned char> img(bytes, 0);
     int* L = reinterpret_cast<int*>(img.data());
     int* C = L + dst;
@@ -294,6 +297,11 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
             P[4 * u + 3] = h.cleft[u] + (swap ? 0 : 1);
         }
     }
+    if (tbytes) {
+        double* T = reinterpret_cast<double*>(img.data() + toff);
+        for (unsigned u = 0; u < dst; u++)
+            for (int i = 0; i < h.cwin; i++) T[(size_t)i * dst + u] = h.cw[(size_t)u * h.cwin + i];
+    }
     cudaError_t e = cudaMalloc(&t->dev, bytes);
     if (e != cudaSuccess) { delete t; return fail_cuda(ctx, e, "cudaMalloc(table)"); }
     e = cudaMemcpyAsync(t->dev, img.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
@@ -309,6 +317,7 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     t->view.cleft = h.compact ? t->view.left + 3 * dst : nullptr;
     t->view.cw    = h.compact ? reinterpret_cast<const double*>(base + ints_al + 2 * wbytes) : nullptr;
     t->view.cwin  = h.cwin;
+    t->view.cwt   = tbytes ? reinterpret_cast<const double*>(base + toff) : nullptr;
     t->view.exact29 = h.exact29 ? 1 : 0;
     t->view.pow2pair = h.pow2pair ? 1 : 0;
     t->view.pack2 = pbytes ? base + poff : nullptr;
