@@ -97,12 +97,12 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
  * y16 + f * y16_fstride (halves), csrc + f * csrc_fstride (floats). */
 bool prep_chroma_handover(const AxisTableDev& vc, const AxisTableDev& hc);
 /* Second-generation front end for the hand-over route (prep.cu: prep2_kernel): same outputs as launch_prep with csrc given,
- * y32 (optional) = the FP32 interpolated Y plane, row 0 = destination row e0.  fused_mac: one double FMA per tap (product
+ * y32 (optional) = the FP32 interpolated Y plane, row 0 = destination row e0; src_rows = source rows present from src_row0 on.  fused_mac: one double FMA per tap (product
  * mode, Y within ~1e-16 relative of the reference before its rounding to FP32) instead of the reference's separately rounded
  * multiply and add (bit-exact).  pairs_ok = prep2_pairs_ok(host copy of hy.cleft).  Returns 1 launched, 0 not covered, -1 the
  * launch failed. */
 bool prep2_pairs_ok(const int* h_hyl, unsigned ow);
-int launch_prep2(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, unsigned ow, unsigned oh,
+int launch_prep2(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, unsigned src_rows, unsigned ow, unsigned oh,
                  unsigned e0, unsigned e1, float* y32, bool fused_mac, __half* y16, Y16Geom g, unsigned strip_row0,
                  const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc,
                  const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, bool pairs_ok, cudaStream_t s,

@@ -49,6 +49,7 @@ inline bool getenv_flag(const char* name) { const char* e = std::getenv(name); r
 struct PrepParams {
     const uint8_t* src;         /* source row src_row0 */
     unsigned w, src_row0;
+    unsigned src_rows;          /* source rows available from src_row0 on (prep2_kernel: bounds of its L2 prefetch) */
     unsigned ow, oh;
     unsigned e0, e1;            /* destination rows computed */
     float* planes; size_t plane_stride;   /* plane p row 0 = destination row e0 */
@@ -471,6 +472,22 @@ prep2_kernel(const PrepParams p)
     const unsigned x0 = blockIdx.x * TW, gy0 = p.e0 + blockIdx.y * TH;
     const int ny = (int)min((unsigned)TH, p.e1 - gy0), nx = (int)min((unsigned)TW, p.ow - x0);
 
+    /* the source bytes of the tile come straight from HBM, and the exact footprint is only known once the tables have been read:
+     * ask L2 for the approximate footprint now (same magnification on both axes: source = destination * w / ow), so that the
+     * colour-in loads below find their lines in L2 instead of paying a DRAM round trip behind two block barriers */
+    if (tid < 96) {
+        const unsigned scale_num = p.w, scale_den = p.ow;
+        const int r_first = (int)((size_t)gy0 * scale_num / scale_den) - 3, r_last = (int)((size_t)(gy0 + ny) * scale_num / scale_den) + 3;
+        const int c_first = max(0, (int)((size_t)x0 * scale_num / scale_den) - 4);
+        const int row = r_first + tid / 3, k = tid % 3;
+        const int rel = row - (int)p.src_row0;
+        if (row <= r_last && rel >= 0 && rel < (int)p.src_rows) {
+            const size_t off = ((size_t)rel * p.w + (size_t)c_first) * D + (size_t)k * 128;
+            if (off < (size_t)(rel + 1) * p.w * D)                  /* stay inside the row (and with it inside the image) */
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(f_src + off));
+        }
+    }
+
     /* ---- 0. footprint of the tile: rows [rlo, rlo+nr), columns [clo, clo+nc) with clo, nc even; chroma region inside it */
     {
         int lo = INT_MAX, hi = -1, clo_ = INT_MAX, chi_ = -1;
@@ -816,7 +833,7 @@ bool prep2_pairs_ok(const int* h_hyl, unsigned ow)
     return true;
 }
 
-int launch_prep2(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, unsigned ow, unsigned oh,
+int launch_prep2(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, unsigned src_rows, unsigned ow, unsigned oh,
                  unsigned e0, unsigned e1, float* y32, bool fused_mac, __half* y16, Y16Geom g, unsigned strip_row0,
                  const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc,
                  const int* h_vyl, const int* h_vcl, const int* h_hyl, const int* h_hcl, bool pairs_ok, cudaStream_t s,
@@ -829,7 +846,7 @@ int launch_prep2(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, 
     if (y16 && ((g.pitch & 1) || ((uintptr_t)y16 & 3u) || (y16_fstride & 1u))) return 0;
     if (y32 && (((uintptr_t)y32 & 7u))) return 0;
     PrepParams p{};
-    p.src = src; p.w = w; p.src_row0 = src_row0; p.ow = ow; p.oh = oh; p.e0 = e0; p.e1 = e1;
+    p.src = src; p.w = w; p.src_row0 = src_row0; p.src_rows = src_rows; p.ow = ow; p.oh = oh; p.e0 = e0; p.e1 = e1;
     p.planes = y32; p.plane_stride = 0; p.write_y32 = y32 ? 1 : 0;
     p.y16 = y16; p.pitch = g.pitch; p.y16_rows = g.rows; p.strip_row0 = (int)strip_row0;
     p.vyl = vy.cleft; p.vcl = vc.cleft; p.hyl = hy.cleft; p.hcl = hc.cleft;

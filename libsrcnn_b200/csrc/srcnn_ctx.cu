@@ -419,7 +419,7 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
         if (chroma_up && ctx->prep2)
             /* product route: second-generation kernel; one double FMA per tap in tensor mode, the reference's separately rounded
              * multiply and add in bit-exact mode */
-            lp = launch_prep2(d_src, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, y32 ? P_dst : nullptr, tensor,
+            lp = launch_prep2(d_src, p.w, p.d, p.s0, p.s1 - p.s0, p.ow, p.oh, p.e0, p.e1, y32 ? P_dst : nullptr, tensor,
                               tensor ? static_cast<__half*>(ctx->y16.p) : nullptr, g, p.r0,
                               vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
                               hy->host.cleft.data(), hc->host.cleft.data(), hy->pairs_ok, s,
@@ -582,7 +582,7 @@ int run_group(srcnn_b200_ctx* ctx, Plan& p, unsigned G, const uint8_t* d_src, ui
     Stamp st(ctx);                                                  /* timings then describe the whole group */
     int lp = 0;
     if (ctx->prep2)
-        lp = launch_prep2(d_src + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, true, Y16, g, p.r0,
+        lp = launch_prep2(d_src + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.s1 - p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, true, Y16, g, p.r0,
                           vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
                           hy->host.cleft.data(), hc->host.cleft.data(), hy->pairs_ok, s, CS, ps_csrc, G, ib, y16_f, csrc_f);
     if (lp == 0)
