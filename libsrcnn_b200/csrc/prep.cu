@@ -57,7 +57,7 @@ struct PrepParams {
     __half* y16; int pitch, y16_rows; int strip_row0;
     const int *vyl, *vcl, *hyl, *hcl;     /* compact lefts   */
     const double *vyw, *vcw, *hyw, *hcw;  /* compact weights */
-    const double* hywt;                   /* horizontal Y weights transposed [tap][ow] (prep2_kernel) */
+    const double *hywt, *hcwt;            /* horizontal weights transposed [tap][ow] (NULL: not available) */
     int SR, SC;                 /* shared-memory capacity of the source footprint (rows, columns) */
     /* chroma hand-over at SOURCE resolution (chroma mode 2 only, may be NULL): instead of resampling Cb / Cr / A here, the
      * colour-converted FP32 samples of the footprint are written to csrc[plane][(row - src_row0) * w + col] and the x2
@@ -216,10 +216,11 @@ prep_kernel(const PrepParams p)
     int hly = 0, hlc = 0;
     if (col_ok) {
         hly = __ldg(p.hyl + gx); hlc = __ldg(p.hcl + gx);
+        /* tap-major copies of the tables when present: adjacent columns then read adjacent words (see prep2_kernel) */
         #pragma unroll
-        for (int i = 0; i < WY; i++) wy[i] = __ldg(p.hyw + gx * WY + i);
+        for (int i = 0; i < WY; i++) wy[i] = p.hywt ? __ldg(p.hywt + (size_t)i * p.ow + gx) : __ldg(p.hyw + gx * WY + i);
         #pragma unroll
-        for (int i = 0; i < WC; i++) wc[i] = __ldg(p.hcw + gx * WC + i);
+        for (int i = 0; i < WC; i++) wc[i] = p.hcwt ? __ldg(p.hcwt + (size_t)i * p.ow + gx) : __ldg(p.hcw + gx * WC + i);
     }
 
     if (tid == 0) { s_lim[0] = INT_MAX; s_lim[1] = -1; s_lim[2] = INT_MAX; s_lim[3] = -1; }
@@ -851,7 +852,7 @@ int launch_prep2(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, 
     p.y16 = y16; p.pitch = g.pitch; p.y16_rows = g.rows; p.strip_row0 = (int)strip_row0;
     p.vyl = vy.cleft; p.vcl = vc.cleft; p.hyl = hy.cleft; p.hcl = hc.cleft;
     p.vyw = vy.cw; p.vcw = vc.cw; p.hyw = hy.cw; p.hcw = hc.cw;
-    p.hywt = hy.cwt;
+    p.hywt = hy.cwt; p.hcwt = hc.cwt;
     if (!p.hywt) return 0;
     p.SR = max_footprint(h_vyl, vy.cwin, h_vcl, vc.cwin, e0, e1, TH);
     p.SC = max_footprint_even(h_hyl, hy.cwin, h_hcl, hc.cwin, 0, ow, TW);
@@ -881,6 +882,7 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
     p.y16 = y16; p.pitch = g.pitch; p.y16_rows = g.rows; p.strip_row0 = (int)strip_row0;
     p.vyl = vy.cleft; p.vcl = vc.cleft; p.hyl = hy.cleft; p.hcl = hc.cleft;
     p.vyw = vy.cw; p.vcw = vc.cw; p.hyw = hy.cw; p.hcw = hc.cw;
+    p.hywt = hy.cwt; p.hcwt = hc.cwt;
     p.SR = max_footprint(h_vyl, vy.cwin, h_vcl, vc.cwin, e0, e1, TH);
     p.SC = max_footprint(h_hyl, hy.cwin, h_hcl, hc.cwin, 0, ow, TW);
     /* chroma arithmetic: 2 = FP32 two-tap (pow2pair tables), 1 = FP64 fused multiply-add (exact29), 0 = FP64 mul + add */
