@@ -369,7 +369,7 @@ def measure(env, name, steps, warmup, arg_frames=0, want_e2e=True, want_dropin=F
     fe_ms = stage_avg["color_in"] + stage_avg["resize1"] + stage_avg["resize2"] + stage_avg["pack"]
     fe_bytes = src_px * d + halo_px * 2 + src_px * 4 * (d - 1)
     co_bytes = unit_px * 4 + src_px * 4 * (d - 1) + unit_px * (d + (1 if conv_on else 0))
-    if m != 2.0:                                                   # no x2 hand-over: chroma / alpha planes at output size
+    if m < 1.5:                                                    # no hand-over below x1.5: chroma / alpha planes at output size
         fe_bytes = src_px * d + halo_px * 2 + halo_px * 4 * (d - 1)
         co_bytes = unit_px * 4 * d + unit_px * (d + (1 if conv_on else 0))
     res["mem_kernels"] = [("front end (colour-in + Y resize + conv-input pack + chroma hand-over)", fe_bytes, fe_ms),

@@ -47,7 +47,8 @@ struct AxisTableDev {
     const double* cwt;      /* compact weights transposed: [cwin][dst] (16-byte aligned; NULL without the compact form) */
     int           exact29;  /* all weights have <= 29 significant bits: fma == mul, add */
     int           pow2pair; /* cwin == 2, both weights exact in FP32, one of each pair 0 or a power of two (prep.cu) */
-    const void*   pack2;    /* pow2pair only: [dst] int4 { left + idx(tap A), bits(wA), bits(wB), left + idx(tap B) } (color.cu) */
+    const void*   pack2;    /* cwin == 2 only: [dst] int4 { left + idx(tap A), bits(wA), bits(wB), left + idx(tap B) } with the weights as
+                               FP32 (exact for pow2pair tables, rounded otherwise) (color.cu) */
 };
 
 /* geometry of the FP16 conv-input plane consumed by the tensor-core kernel (see DESIGN.md "Y16 plane") */
@@ -95,7 +96,10 @@ int launch_prep(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, u
  * for launch_color_out_up to resample.  prep_chroma_handover() tells whether a set of tables takes that route.
  * nframes > 1 (hand-over route only): a group of same-geometry frames in one launch, frame f at src + f * src_fstride (bytes),
  * y16 + f * y16_fstride (halves), csrc + f * csrc_fstride (floats). */
-bool prep_chroma_handover(const AxisTableDev& vc, const AxisTableDev& hc);
+/* approx_ok (tensor-core conv mode only): any pair of two-tap chroma tables qualifies -- colour-out then resamples with one FP32
+ * fused multiply-add per tap pair, which is the correctly rounded exact sum for the power-of-two tables (x2) and within ~1e-7
+ * relative of the reference's double accumulation otherwise (other magnifications; the gate there is the final 1 LSB / 50 dB) */
+bool prep_chroma_handover(const AxisTableDev& vc, const AxisTableDev& hc, bool approx_ok);
 /* Second-generation front end for the hand-over route (prep.cu: prep2_kernel): same outputs as launch_prep with csrc given,
  * y32 (optional) = the FP32 interpolated Y plane, row 0 = destination row e0; src_rows = source rows present from src_row0 on.  fused_mac: one double FMA per tap (product
  * mode, Y within ~1e-16 relative of the reference before its rounding to FP32) instead of the reference's separately rounded

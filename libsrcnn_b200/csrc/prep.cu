@@ -524,7 +524,7 @@ prep2_kernel(const PrepParams p)
      * pair and walks down the rows in steps of RL, so everything but the row is loop-invariant.  All of a thread's source
      * words (at most NI rows) are requested before the first one is used: the stage is bound by load latency otherwise */
     {
-        constexpr int NI = 4;                                     /* rows per thread: nr <= NI * RL (checked on the host) */
+        constexpr int NI = (28 + RL - 1) / RL;                    /* rows per thread: nr <= 28 <= NI * RL (checked on the host) */
         const int cp = tid % NCP, rl = tid / NCP;
         if (rl < RL && cp < ncp) {
             const int col = clo + 2 * cp;
@@ -779,10 +779,9 @@ int max_footprint_even(const int* ly, int wy, const int* lc, int wc, unsigned d0
     return best;
 }
 
-template <int D, int WY, bool FMA>
-int launch_prep2(const PrepParams& p, dim3 grid, cudaStream_t s)
+template <int D, int WY, bool FMA, int SC>
+int launch_prep2_sc(const PrepParams& p, dim3 grid, cudaStream_t s)
 {
-    constexpr int SC = 72;
     static std::atomic<bool> configured[kMaxDevices];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return 0; }
@@ -798,6 +797,13 @@ int launch_prep2(const PrepParams& p, dim3 grid, cudaStream_t s)
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
+/* shared-memory row pitch (doubles): 72 covers magnifications >= 2, 104 those >= 1.5 */
+template <int D, int WY, bool FMA>
+int launch_prep2(const PrepParams& p, dim3 grid, cudaStream_t s)
+{
+    return p.SC <= 72 ? launch_prep2_sc<D, WY, FMA, 72>(p, grid, s) : launch_prep2_sc<D, WY, FMA, 104>(p, grid, s);
+}
+
 template <int D, bool FMA>
 int launch_prep2_wy(const PrepParams& p, int wy, dim3 grid, cudaStream_t s)
 {
@@ -811,9 +817,11 @@ int launch_prep2_wy(const PrepParams& p, int wy, dim3 grid, cudaStream_t s)
 
 } // namespace
 
-bool prep_chroma_handover(const AxisTableDev& vc, const AxisTableDev& hc)
+bool prep_chroma_handover(const AxisTableDev& vc, const AxisTableDev& hc, bool approx_ok)
 {
-    return vc.pow2pair && hc.pow2pair && !getenv_flag("SRCNN_B200_PREP_F64");
+    if (getenv_flag("SRCNN_B200_PREP_F64")) return false;
+    if (vc.pow2pair && hc.pow2pair) return true;
+    return approx_ok && vc.pack2 && hc.pack2 && !getenv_flag("SRCNN_B200_CHROMA_EXACT");
 }
 
 bool prep_supported(const AxisTableDev& vy, const AxisTableDev& vc, const AxisTableDev& hy, const AxisTableDev& hc)
@@ -842,7 +850,7 @@ int launch_prep2(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, 
 {
     if (!csrc || !pairs_ok || (w & 1u) || (ow & 1u) || (csrc_stride & 1u) || (csrc_fstride & 1u) || (d != 3 && d != 4)) return 0;
     if (((uintptr_t)src & 7u) || ((src_fstride) & 7u) || ((uintptr_t)csrc & 7u)) return 0;
-    if (!prep_supported(vy, vc, hy, hc) || !prep_chroma_handover(vc, hc)) return 0;
+    if (!prep_supported(vy, vc, hy, hc) || !prep_chroma_handover(vc, hc, fused_mac)) return 0;
     if (nframes > 1 && y32) return 0;
     if (y16 && ((g.pitch & 1) || ((uintptr_t)y16 & 3u) || (y16_fstride & 1u))) return 0;
     if (y32 && (((uintptr_t)y32 & 7u))) return 0;
@@ -856,7 +864,7 @@ int launch_prep2(const uint8_t* src, unsigned w, unsigned d, unsigned src_row0, 
     if (!p.hywt) return 0;
     p.SR = max_footprint(h_vyl, vy.cwin, h_vcl, vc.cwin, e0, e1, TH);
     p.SC = max_footprint_even(h_hyl, hy.cwin, h_hcl, hc.cwin, 0, ow, TW);
-    if (p.SC > 72 || p.SR > 28) return 0;                       /* prep2_kernel: SC = 72, at most 4 x 7 footprint rows */
+    if (p.SC > 104 || p.SR > 28) return 0;                      /* prep2_kernel: SC = 72 / 104, at most 28 footprint rows */
     if ((size_t)(oh ? (size_t)w * ((size_t)oh / 1 + 64) : 0) * 4 >= ((size_t)1 << 31)) return 0;       /* 32-bit pixel offsets (source rows <= oh) */
     p.csrc = csrc; p.csrc_stride = csrc_stride;
     p.src_fstride = src_fstride; p.y16_fstride = y16_fstride; p.csrc_fstride = csrc_fstride;

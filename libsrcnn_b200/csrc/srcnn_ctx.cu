@@ -267,7 +267,7 @@ int get_table(srcnn_b200_ctx* ctx, int filter, unsigned dst, unsigned src, Table
     const size_t ints = (size_t)dst * sizeof(int);
     const size_t ints_al = (4 * ints + 15) / 16 * 16;
     const size_t wbytes = h.w.size() * sizeof(double), cbytes = h.cw.size() * sizeof(double);
-    const size_t pbytes = (h.compact && h.pow2pair) ? (size_t)dst * 16 : 0;       /* pack2 (color.cu) */
+    const size_t pbytes = (h.compact && h.cwin == 2) ? (size_t)dst * 16 : 0;      /* pack2 (color.cu): every two-tap table */
     const size_t poff = (ints_al + 2 * wbytes + cbytes + 15) / 16 * 16;
     /* cwt: the compact weights transposed, [tap][dst] -- adjacent destination samples are adjacent in memory, so a warp reading
      * one tap of its 64 columns touches 512 contiguous bytes instead of 32 scattered 64-byte-strided words (prep.cu: prep2_kernel) */
@@ -411,7 +411,7 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
     if (ctx->fuse_front && !p.hfirst && p.need_h && p.need_v && prep_supported(vy->view, vc->view, hy->view, hc->view)) {
         /* x2-type magnification: Cb / Cr / A stay at source resolution and are resampled inside colour-out (the output-size
          * chroma planes then never exist -- unless the plane getters were asked to keep them) */
-        chroma_up = ctx->chroma_up && ctx->keep_planes != 1 && !(tensor && ctx->fuse_color) && prep_chroma_handover(vc->view, hc->view) && (p.ow % 4) == 0 &&
+        chroma_up = ctx->chroma_up && ctx->keep_planes != 1 && !(tensor && ctx->fuse_color) && prep_chroma_handover(vc->view, hc->view, tensor) && (p.ow % 4) == 0 &&
                     hc->quads_ok && ((uintptr_t)d_out % (p.d == 4 ? 16 : 4)) == 0 &&
                     (!d_conv || ((uintptr_t)d_conv % 4) == 0);
         if (chroma_up) CK(ctx->chroma_src.ensure(ps_csrc * (p.d - 1) * sizeof(float)));
@@ -424,6 +424,8 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
                               vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
                               hy->host.cleft.data(), hc->host.cleft.data(), hy->pairs_ok, s,
                               static_cast<float*>(ctx->chroma_src.p), ps_csrc);
+        /* (the first-generation kernel hands chroma over only for the exact, power-of-two tables) */
+        if (lp == 0 && chroma_up && !prep_chroma_handover(vc->view, hc->view, false)) chroma_up = false;
         if (lp == 0)
           lp = launch_prep(d_src, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, P_dst, ps_dst, y32,
                                    tensor ? static_cast<__half*>(ctx->y16.p) : nullptr, g, p.r0,
@@ -565,7 +567,7 @@ int run_group(srcnn_b200_ctx* ctx, Plan& p, unsigned G, const uint8_t* d_src, ui
     if ((rc = get_table(ctx, p.fc, p.ow, p.w, &hc))) return rc;
     source_rows(vy->host, vc->host, p.e0, p.e1, p.s0, p.s1);
     const size_t ib = (size_t)p.w * p.h * p.d, ob = (size_t)p.ow * p.oh * p.d, cb = (size_t)p.ow * p.oh;
-    if (!prep_supported(vy->view, vc->view, hy->view, hc->view) || !prep_chroma_handover(vc->view, hc->view) || !hc->quads_ok ||
+    if (!prep_supported(vy->view, vc->view, hy->view, hc->view) || !prep_chroma_handover(vc->view, hc->view, true) || !hc->quads_ok ||
         ((uintptr_t)d_out % 16) || (ob % 16) || (d_conv && (((uintptr_t)d_conv % 4) || (cb % 4)))) return 1;
     auto al = [](size_t n) { return (n + 63) / 64 * 64; };
     const unsigned srows = p.s1 - p.s0;
@@ -585,6 +587,7 @@ int run_group(srcnn_b200_ctx* ctx, Plan& p, unsigned G, const uint8_t* d_src, ui
         lp = launch_prep2(d_src + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.s1 - p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, true, Y16, g, p.r0,
                           vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(), vc->host.cleft.data(),
                           hy->host.cleft.data(), hc->host.cleft.data(), hy->pairs_ok, s, CS, ps_csrc, G, ib, y16_f, csrc_f);
+    if (lp == 0 && !prep_chroma_handover(vc->view, hc->view, false)) return 1;      /* (approximate hand-over: second-generation kernel only) */
     if (lp == 0)
       lp = launch_prep(d_src + (size_t)p.s0 * p.w * p.d, p.w, p.d, p.s0, p.ow, p.oh, p.e0, p.e1, nullptr, 0, false,
                                Y16, g, p.r0, vy->view, vc->view, hy->view, hc->view, vy->host.cleft.data(),

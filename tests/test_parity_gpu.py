@@ -661,3 +661,45 @@ def test_cuda_graph_replay_equals_plain_launches(ctx):
             assert np.array_equal(d_out[100:].cpu().numpy(), want2[100:])
     finally:
         ctx.set_graphs(False)
+
+
+@pytest.mark.parametrize("m,filt,d,hw", [(1.5, S.BSPLINE, 3, (120, 200)), (2.5, S.BICUBIC, 4, (64, 96)), (3.0, S.LANCZOS3, 3, (60, 80)),
+                                         (1.75, S.BILINEAR, 3, (96, 128))])
+def test_chroma_handover_at_other_magnifications(m, filt, d, hw):
+    """tensor mode, magnification >= 1.5 other than x2: Cb / Cr / A are handed over at source resolution as well and resampled inside
+    colour-out with FP32 two-tap arithmetic (approximate there -- the weights are not powers of two -- and gated by the final
+    1 LSB / 50 dB); SRCNN_B200_CHROMA_EXACT=1 and the bit-exact conv mode keep the reference's double arithmetic on output-size planes"""
+    import os
+    h, w = hw
+    img = O.synth("uniform", h, w, d, 97)
+    rc, want, want_conv = O.best().process(img, m, filt, False, True)
+    assert rc == 0
+    ow, oh = S.output_dims(w, h, m)
+    c = S.Context(0, S.CONV_TENSOR)
+    out, conv = c.pass_host(img, m, filt, True)
+    _check_u8("rgb", out, want.reshape(oh, ow, d), False)
+    _check_u8("conv", conv, want_conv.reshape(oh, ow), False)
+    if ow % 4 == 0:
+        with pytest.raises(S.SrcnnError):
+            c.get_plane(1, (oh, ow))                      # product route: no output-size chroma planes
+    # strips of the product route equal the full image
+    r0, r1 = oh // 3, oh // 3 + max(1, oh // 4)
+    so, sc = c.pass_host(img, m, filt, True, rows=(r0, r1))
+    assert np.array_equal(so, out[r0:r1]) and np.array_equal(sc, conv[r0:r1])
+    # bit-exact mode never takes the approximate route
+    c.set_conv_mode(S.CONV_EXACT)
+    ex, exconv = c.pass_host(img, m, filt, True)
+    _check_u8("exact rgb", ex, want.reshape(oh, ow, d), True)
+    c.close()
+    os.environ["SRCNN_B200_CHROMA_EXACT"] = "1"
+    try:
+        c2 = S.Context(0, S.CONV_TENSOR)
+        out2, _ = c2.pass_host(img, m, filt, False)
+        c2.get_plane(1, (oh, ow))                         # the planes exist on this route
+        c2.close()
+    finally:
+        os.environ.pop("SRCNN_B200_CHROMA_EXACT", None)
+    _check_u8("rgb (exact chroma route)", out2, want.reshape(oh, ow, d), False)
+    # the two routes differ only where an FP32-rounded chroma sample crosses a truncation boundary
+    assert (np.abs(out.astype(int) - out2.astype(int)) > 1).sum() == 0
+    assert (out != out2).mean() < 0.01
