@@ -158,7 +158,7 @@ constexpr int kUpBlockPx = 1024;              /* output pixels of one row per CT
 constexpr int kUpWarpPx = 128;                /* ... per warp */
 constexpr int kUpIters = 3;                   /* staging passes of 32 columns */
 constexpr int kUpMaxCols = 32 * kUpIters;     /* source columns a warp may need: magnification >= ~1.37 (x2: 66) */
-constexpr int kUpRowsMax = 48;                /* consecutive output rows per CTA (the horizontal table entries stay in registers);
+constexpr int kUpRowsMax = 16;                /* consecutive output rows per CTA (the horizontal table entries stay in registers);
                                                  fewer for small images so that the grid still fills the SMs */
 
 __device__ __forceinline__ int up_pos(int j) { return (j >> 1) + (j & 1) * (kUpMaxCols / 2); }
@@ -297,11 +297,12 @@ bool launch_color_out_up(const float* yp, const float* csrc, size_t cstride, uns
     if (cstride * (size_t)(d - 1) >= ((size_t)1 << 30)) return false;       /* 32-bit element offsets into the chroma planes */
     if (!al(yp, 16) || !al(out, d == 4 ? 16 : 4) || (conv && !al(conv, 4))) return false;
     const unsigned gx = (ow + kUpBlockPx - 1) / kUpBlockPx * nframes, nrows = row1 - row0;   /* (x nframes: for the wave estimate) */
-    /* rows per CTA: 4 CTAs of <= 64 registers x 256 threads are resident per SM (3 of the RGBA instantiations, 73-79 registers);
-     * pick the row count that minimises (number of waves) x (rows + one row-time of prologue), i.e. avoids a nearly empty last
-     * wave -- with a strip of ~1000 rows the kernel is only one to four waves long, so this is worth 15 % */
+    /* rows per CTA: pick the row count that minimises (number of waves of 4 CTAs per SM) x (rows + one row-time of prologue), i.e.
+     * avoids a nearly empty last wave.  (Measured, round 2: modelling the RGBA instantiations' real residency of 3 CTAs per SM and
+     * allowing up to 48 rows per CTA picks one wave of 38-row CTAs for a 1080-row strip and is SLOWER -- 53 vs 50 us -- than two
+     * short waves of 16-row CTAs: CTAs are scheduled dynamically, many short ones balance better than the wave model predicts.) */
     const int sms = num_sms > 0 ? num_sms : 148;
-    const size_t resident = (size_t)sms * (d == 4 ? 3 : 4);
+    const size_t resident = (size_t)sms * 4;
     unsigned rpc = 2; size_t best = ~(size_t)0;
     for (unsigned r = 2; r <= (unsigned)kUpRowsMax; r++) {
         const size_t ctas = (size_t)gx * ((nrows + r - 1) / r), waves = (ctas + resident - 1) / resident;
