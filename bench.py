@@ -180,7 +180,20 @@ def cpu_baseline_leg(name, ctx, budget_s=25.0):
         if conv is not None:
             dc = np.abs(gconv.reshape(-1).astype(np.int16) - conv.astype(np.int16))
             par["conv_max_abs_lsb"] = int(dc.max()); ok = ok and bool(dc.max() <= 1)
-        par.update(gate="<= 1 LSB and >= 50 dB, GPU (tensor path) against the CPU result of the same full frame", ok=ok)
+        # the interpolated Y plane of the product route (FP32 copy written on request) against the reference's resize: 1e-5 relative
+        try:
+            ctx.set_keep_planes(2)
+            ctx.pass_host(img, m, filt, False)
+            _, gy = ctx.get_plane(0, (oh, ow))
+            ctx.set_keep_planes(False)
+            ry = orc.resize(orc.color_in(img)[0], ow, oh, filt)
+            rel = float((np.abs(gy - ry) / np.maximum(np.abs(ry), 1.0)).max())
+            par["y_plane_rel_max"] = rel; par["y_plane_differing_samples"] = int((gy != ry).sum())
+            ok = ok and rel <= 1e-5
+        except Exception as e:                                              # noqa: BLE001
+            par["y_plane_rel_max"] = None; par["y_plane_note"] = repr(e)
+        par.update(gate="final image (and conv plane) <= 1 LSB and >= 50 dB, interpolated Y plane <= 1e-5 relative: GPU (tensor path) "
+                        "against the CPU result of the same full frame", ok=ok)
         res["parity"] = par
     return res
 
