@@ -118,8 +118,23 @@ constexpr int CH_BYTES = CH_ROWS * BOX_W * 2;
 
 /* warp roles: one control warpgroup + five 4-warp groups (TMEM lane quarter = warp & 3); the order of the groups made no
  * measurable difference on B200 */
-constexpr int W_E3 = 0, W_E2 = 4, W_E1 = 8, W_IM2COL = 16, W_CTL = 20, NWARPS = 24;
-constexpr int W_TMA = W_CTL, W_MMA1 = W_CTL + 1, W_MMA2 = W_CTL + 2, W_MMA3 = W_CTL + 3;
+/* SRCNN_ISSUE_SPLIT = 1: the conv I and conv II issuers are split by row parity (a second control warpgroup: warps 24 / 25 issue
+ * the odd rows, 26 / 27 idle).  An issuer's per-row loop is serial -- observe the operand barrier, fence, elect, ~10 uniform-register
+ * moves, the MMAs, commit, reconverge: ~220 clk per batch on an idle SM (tools/probe/mma_victim.cu), ~340 clk inside this kernel
+ * (wait profile: the conv I issuer is outside its barrier wait 66 % of the time) -- and with one warp per layer every row of the
+ * CTA passes through it. */
+#ifndef SRCNN_ISSUE_SPLIT
+#define SRCNN_ISSUE_SPLIT 0
+#endif
+constexpr int W_E3 = 0, W_E2 = 4, W_E1 = 8, W_IM2COL = 16, W_CTL = 20, W_CTL2 = 24, NWARPS = SRCNN_ISSUE_SPLIT ? 28 : 24;
+constexpr int W_MMA1B = W_CTL2, W_MMA2B = W_CTL2 + 1;
+/* SRCNN_CTLPERM: sub-partition (= warp index within the control warpgroup) of the TMA producer and the three issuers, one hex
+ * digit each: 0x3210 = TMA 0, conv I 1, conv II 2, conv III 3 */
+#ifndef SRCNN_CTLPERM
+#define SRCNN_CTLPERM 0x3210
+#endif
+constexpr int W_TMA = W_CTL + (SRCNN_CTLPERM & 15), W_MMA1 = W_CTL + ((SRCNN_CTLPERM >> 4) & 15), W_MMA2 = W_CTL + ((SRCNN_CTLPERM >> 8) & 15),
+              W_MMA3 = W_CTL + ((SRCNN_CTLPERM >> 12) & 15);
 
 /* barrier indices.  M?_DONE[b] fires when the MMAs of layer ? for a row with parity b have completed: it both frees the
  * A operand region for the producer group and publishes the accumulator to the consumer group. */
@@ -183,13 +198,29 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
 }
+/* SRCNN_WAITMODE: 0 = try_wait with a suspend-time hint (compiles to TRYWAIT / NANOSLEEP.SYNCS / PHASECHK / BRA), 1 = plain try_wait
+ * loop (TRYWAIT / BRA), 2 = try_wait + nanosleep back-off */
+#ifndef SRCNN_WAITMODE
+#define SRCNN_WAITMODE 0
+#endif
+#ifndef SRCNN_WAITNS
+#define SRCNN_WAITNS 32
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    /* the suspend-time hint keeps a waiting warp asleep in the barrier unit instead of re-issuing the probe: without it
-     * ~28 % of all issued instructions of this kernel were retry loops competing with the working warps */
+#if SRCNN_WAITMODE == 0
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
                  "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+#elif SRCNN_WAITMODE == 1
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(bar), "r"(parity) : "memory");
+#else
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nnanosleep.u32 %2;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(bar), "r"(parity), "n"(SRCNN_WAITNS) : "memory");
+#endif
 }
 /* latency-critical waits (the single-lane MMA issuers): poll instead of suspending -- a suspended warp resumes noticeably
  * later than the phase flips, and that wake-up latency sits on every operand / accumulator hand-over of the pipeline */
@@ -198,6 +229,13 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
                  "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
                  "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+/* uncritical waits (the TMA producer runs up to four 8-row chunks ahead): back off between probes */
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nnanosleep.u32 256;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
@@ -304,6 +342,37 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane)
 #define WAITP(id, bar, par) mbar_wait(bar, par)
 #define WAITS(site, id, bar, par) do { if ((SRCNN_SPINMASK >> (site)) & 1) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
 #endif
+/* SRCNN_TL (development build): CTA 0 records clock64() of the pipeline events of TL_N consecutive rows starting at row TL_R0
+ * (CTA-global row counter) into p.prof[row][32]; tools/conv_timeline.py reads the dump and attributes every tensor-pipe gap */
+#ifdef SRCNN_TL
+#ifndef SRCNN_TL_CTA
+#define SRCNN_TL_CTA 0
+#endif
+constexpr int TL_R0 = 96, TL_N = 128, TL_W = 128;      /* per row: 32 events x 4 warps of a group */
+#define TL(ev, rowidx, cond) do { const int r_ = (int)(rowidx) - TL_R0; \
+    if (blockIdx.x == SRCNN_TL_CTA && (threadIdx.x & 31) == 0 && r_ >= 0 && r_ < TL_N) p.prof[r_ * TL_W + (ev) * 4 + ((threadIdx.x >> 5) & 3)] = clock64(); } while (0)
+#define TLI(ev, rowidx) do { const int r_ = (int)(rowidx) - TL_R0; \
+    if (blockIdx.x == SRCNN_TL_CTA && r_ >= 0 && r_ < TL_N) p.prof[r_ * TL_W + (ev) * 4] = clock64(); } while (0)
+#else
+#define TL(ev, rowidx, cond) ((void)0)
+#define TLI(ev, rowidx) ((void)0)
+#endif
+/* SRCNN_GWAIT = 1: only ONE warp of a four-warp group polls an mbarrier; its three siblings block in a named barrier until the
+ * poller joins them.  mbarrier.try_wait does not really suspend a warp on this part: with or without a suspend-time hint the retry
+ * loop (TRYWAIT / NANOSLEEP.SYNCS / PHASECHK / BRA) spins, and ncu's source page showed ~50 M of the kernel's 116 M issued warp
+ * instructions in those loops -- 86 % of all issue slots taken, every working warp slowed to ~10 clk per instruction
+ * (tools/conv_timeline.py).  bar.sync waits cost no issue slots.  SRCNN_LEADS: which warp of each group polls, one hex digit per
+ * group (gather, epilogue II, epilogue I odd, epilogue I even, im2col) -- spread over the sub-partitions next to the issuers. */
+#ifndef SRCNN_GWAIT
+#define SRCNN_GWAIT 0
+#endif
+#ifndef SRCNN_LEADS
+#define SRCNN_LEADS 0x10320
+#endif
+constexpr int NB_IM = 8, NB_E1 = 9, NB_E2 = 11, NB_G = 12;          /* named barriers of the group waits (E1: 9 + parity) */
+__device__ __forceinline__ void named_sync(uint32_t id) { asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory"); }
+#define GWAITS(lead, nb, site, id, bar, par) do { if (!SRCNN_GWAIT || (lead)) WAITS(site, id, bar, par); if (SRCNN_GWAIT) named_sync(nb); } while (0)
+#define GWAITP(lead, nb, id, bar, par) do { if (!SRCNN_GWAIT || (lead)) WAITP(id, bar, par); if (SRCNN_GWAIT) named_sync(nb); } while (0)
 /* 1: im2col rewrites only the two ring slots (10 TMEM columns) that changed since the same-parity row two rows earlier */
 #ifndef SRCNN_A1_PARTIAL
 #define SRCNN_A1_PARTIAL 1
@@ -322,7 +391,7 @@ struct TcParams {
                                    f * y16_rows, its Y' at out + f * out_fstride */
     size_t out_fstride;
     const unsigned char* wimg;  /* B1 x 9 rotations | B2 | B2-bias | B3 operand images */
-#ifdef SRCNN_PROF
+#if defined(SRCNN_PROF) || defined(SRCNN_TL)
     long long* prof;
 #endif
 };
@@ -429,7 +498,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);     /* this warp's TMEM lane quarter */
     const Span span = span_of(p);
 
-    if (warp >= W_CTL && warp < W_CTL + 4) {
+    if (warp >= W_CTL) {
         /* ============================ control warpgroup: TMA producer + three MMA issuers ==================== */
         reg_dec<48>();                      /* the setmaxnreg pool is what the dec's release: 4096 + 2048 + 2048 regs */
         if (warp == W_TMA) {
@@ -442,7 +511,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 const int nch = (un.nrows + 8 + CH_ROWS - 1) / CH_ROWS;
                 for (int j = 0; j < nch; j++, ck++) {
                     const uint32_t s = ck % NST, k = ck / NST;
+#if SRCNN_GWAIT && !defined(SRCNN_PROF)
+                    mbar_wait_sleep(BAR(Y_EMPTY + s), (k & 1) ^ 1);
+#else
                     WAITP(0, BAR(Y_EMPTY + s), (k & 1) ^ 1);
+#endif
                     if (elect_one()) {
                         mbar_expect_tx(BAR(Y_FULL + s), CH_BYTES);
                         tma_load_2d(sY + s * CH_BYTES, &ymap, x0, yr0 + j * CH_ROWS, BAR(Y_FULL + s));
@@ -452,7 +525,10 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             }
         } else if (SRCNN_PI) {
             /* (the producer groups issue their own MMAs; these three warps only wait for the end of the kernel) */
-        } else if (warp == W_MMA1) {
+        } else if (warp >= W_CTL2 + 2) {
+            /* (idle: completes the second control warpgroup) */
+        } else if (warp == W_MMA1 || warp == W_MMA1B) {
+            const uint32_t myb = warp == W_MMA1B;
             ISSUER_BEGIN
             /* conv I: the A1 window is a ring of 9 row slots, so the weight image rotates with the row (R = n mod 9) */
             const uint32_t db0 = (uint32_t)umma_desc(sW, 128, (K1 / 8) * 128);
@@ -466,10 +542,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     const uint32_t ph = pr & 1;
                     #pragma unroll
                     for (uint32_t b = 0; b < 2; b++) {
+                        if (SRCNN_ISSUE_SPLIT && b != myb) { R = (R == NROT - 1) ? 0 : R + 1; continue; }
+                        if (ISSUE_LANE()) TLI(22, 2 * pr + b);
                         WAITS(0, 0, BAR(A1_FULL + b), ph);
                         if (!SRCNN_MERGE_BAR) WAITS(1, 1, BAR(D1_EMPTY + b), ph ^ 1);
                         tc_fence_after();
                         if (ISSUE_LANE()) {
+                            TLI(3, 2 * pr + b);
                             const uint32_t db = db0 + R * (B1_BYTES >> 4);
 #if SRCNN_A1_EARLY
                             /* window rows 0 and 1 of this output row sit in ring slots R and R+1 (mod 9), columns 5R .. 5R+9
@@ -483,18 +562,27 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                             }
 #else
                             #pragma unroll
-                            for (int s = 0; s < K1 / 16; s++)
+                            for (int s = 0; s < K1 / 16; s++) {
+#ifdef SRCNN_DIAG_M1TWO
+                                if (s > 1) continue;
+#endif
                                 umma_ts(tmem + D1_COL + b * D1_STR, tmem + A1_COL + b * A1_STR + 8 * s, db + 16 * s, dh1, umma_idesc(N1), s > 0);
+                            }
 #endif
                             umma_commit(BAR(M1_DONE + b));
+                            TLI(4, 2 * pr + b);
                         }
                         ISSUE_SYNC();
+#ifdef SRCNN_TL
+                        if (ISSUE_LANE()) TLI(25, 2 * pr + b);
+#endif
                         R = (R == NROT - 1) ? 0 : R + 1;
                     }
                 }
             }
             ISSUER_END
-        } else if (warp == W_MMA2) {
+        } else if (warp == W_MMA2 || warp == W_MMA2B) {
+            const uint32_t myb = warp == W_MMA2B;
             ISSUER_BEGIN
             const uint32_t db = (uint32_t)umma_desc(sW + W_B2, 128, (K2 / 8) * 128);
             const uint32_t dbb = (uint32_t)umma_desc(sW + W_B2B, 128, 256);
@@ -505,16 +593,24 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 const uint32_t ph = (g >> 1) & 1;
                 #pragma unroll
                 for (uint32_t b = 0; b < 2; b++) {
+                    if (SRCNN_ISSUE_SPLIT && b != myb) continue;
+                    if (ISSUE_LANE()) TLI(23, g + b);
                     WAITS(4, 0, BAR(A2_FULL + b), ph);
                     if (!SRCNN_MERGE_BAR) WAITS(5, 1, BAR(D2_EMPTY + b), ph ^ 1);
                     tc_fence_after();
                     if (ISSUE_LANE()) {
+                        TLI(9, g + b);
+#ifdef SRCNN_DIAG_M2ONE
+                        umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR, db, dh2, umma_idesc(N2), 0);
+#else
                         #pragma unroll
                         for (int s = 0; s < K2 / 16; s++)
                             umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR + 8 * s, db + 16 * s, dh2, umma_idesc(N2), s > 0);
                         if (!SRCNN_BIAS2_EPI)
                             umma_ts(tmem + D2_COL + b * D2_STR, tmem + A1_COL + b * A1_STR + ABIAS_OFF, dbb, dhb, umma_idesc(N2), 1);     /* + bias */
+#endif
                         umma_commit(BAR(M2_DONE + b));
+                        TLI(10, g + b);
                     }
                     ISSUE_SYNC();
                 }
@@ -540,10 +636,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                         WAITS(8, 0, BAR(A3_FULL) + 8u * (kg0 & 3), (kg0 >> 2) & 1);
                         WAITS(8, 0, BAR(A3_FULL) + 8u * ((kg0 + 1) & 3), ((kg0 + 1) >> 2) & 1);
                     }
+                    if (ISSUE_LANE()) TLI(24, 2 * sg + 4);
                     WAITS(8, 0, BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
+                    if (ISSUE_LANE()) TLI(14, 2 * sg + 4);
                     WAITS(9, 1, BAR(D3_EMPTY + (sg & 1)), ((sg >> 1) & 1) ^ 1);
                     tc_fence_after();
                     if (ISSUE_LANE()) {
+                        TLI(15, 2 * sg + 4);
                         const int r0 = un.ra + 2 * pp;
                         const uint32_t d3 = tmem + D3_COL + (sg & 1) * D3_STR;
                         if (r0 >= 2 && r0 + 3 < p.dh) {
@@ -555,8 +654,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                             for (int j = 0; j < 3; j++) {
                                 const uint32_t pa = tmem + A3_COL + ((kp + j) & 3u) * (2 * A3_SLOT);
                                 #pragma unroll
-                                for (int h = 0; h < 4; h++)
+                                for (int h = 0; h < 4; h++) {
+#ifdef SRCNN_DIAG_M3ONE
+                                    if ((j | h) > 0) continue;
+#endif
                                     umma_ts(d3, pa + 8 * h, db3 + (uint32_t)((4 * j + h) * (B3_TILE >> 4)), dh3, umma_idesc(N3), (j | h) > 0);
+                                }
+                                TLI(26 + j, 2 * sg + 4);
                             }
                         } else {
                             #pragma unroll
@@ -576,6 +680,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                             umma_commit(BAR(A3_EMPTY) + 8u * ((kg0 + (uint32_t)pp + 1) & 3));
                             umma_commit(BAR(A3_EMPTY) + 8u * ((kg0 + (uint32_t)pp + 2) & 3));
                         }
+                        TLI(16, 2 * sg + 4);
                     }
                     ISSUE_SYNC();
                 }
@@ -587,6 +692,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         /* ===================== im2col: smem Y16 ring -> 9-slot register ring -> A1 in TMEM ==================== */
         reg_inc<96>();
         const int t = (warp - W_IM2COL) * 32 + lane;
+        const bool lead = (warp & 3) == (SRCNN_LEADS & 15);
         uint32_t it = 0, ck = 0;
 #if SRCNN_PI
         const uint32_t db1_0 = (uint32_t)umma_desc(sW, 128, (K1 / 8) * 128);
@@ -600,13 +706,18 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             uint32_t W[9][5];                                         /* slot s holds Y row (rho mod 9 == s), two halves per word */
             auto fetch = [&](int rho, uint32_t (&w5)[5]) {
                 const uint32_t c = ck + (uint32_t)(rho / CH_ROWS), s = c % NST;
-                if ((rho % CH_ROWS) == 0) WAITP(0, BAR(Y_FULL + s), (c / NST) & 1);
+                if ((rho % CH_ROWS) == 0) GWAITP(lead, NB_IM, 0, BAR(Y_FULL + s), (c / NST) & 1);
                 const uint32_t a = woff + s * CH_BYTES + (uint32_t)(rho % CH_ROWS) * (BOX_W * 2);
+#ifdef SRCNN_DIAG_NOFETCH      /* timing diagnosis only (wrong results): how much of the row period is im2col's fetch? */
+                #pragma unroll
+                for (int j = 0; j < 5; j++) w5[j] = a + j;
+#else
                 uint32_t x[6];
                 #pragma unroll
                 for (int j = 0; j < 6; j++) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[j]) : "r"(a + 4u * j));
                 #pragma unroll
                 for (int j = 0; j < 5; j++) w5[j] = __funnelshift_r(x[j], x[j + 1], sh);
+#endif
                 if ((rho % CH_ROWS) == CH_ROWS - 1 || rho == last_rho) warp_arrive(BAR(Y_EMPTY + s), lane);
             };
             /* Y row y always lives in slot (y + 6) mod 9, i.e. the k position of a tap depends on the absolute image row only
@@ -619,14 +730,16 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 fetch(n + 8, W[(R + 8) % 9]);
                 if (n < 0) return;
                 const uint32_t b = it & 1, ph = (it >> 1) & 1;
+                TL(0, it, t == 0);
 #if SRCNN_A1_EARLY && SRCNN_A1_PARTIAL && !SRCNN_PI
                 /* partial rewrite: only the K-steps that read the two oldest window rows of row it-2 must have run */
                 WAITS(2, 1, BAR(A1_FREE) + 8u * b, ph ^ 1);
                 if (n < 2) WAITS(2, 1, BAR(M1_DONE) + 8u * b, ph ^ 1);     /* whole operand rewritten: all of row it-2's MMAs */
 #else
-                WAITS(2, 1, BAR(M1_DONE) + 8u * b, ph ^ 1);         /* MMA1 of row it-2 has consumed A1[b] */
+                GWAITS(lead, NB_IM, 2, 1, BAR(M1_DONE) + 8u * b, ph ^ 1);         /* MMA1 of row it-2 has consumed A1[b] */
 #endif
                 tc_fence_after();
+                TL(1, it, t == 0);
                 const uint32_t dst = lane_base + A1_COL + b * A1_STR;
                 if (!SRCNN_A1_PARTIAL || n < 2) {
                     /* first two rows of a unit: the whole operand (both parity buffers still hold another unit's rows) */
@@ -648,6 +761,10 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     constexpr int SA = (R + 7) % 9, SB = (R + 8) % 9;
                     const uint32_t (&wa)[5] = W[SA];
                     const uint32_t (&wb)[5] = W[SB];
+#ifdef SRCNN_DIAG_NOST      /* timing diagnosis only (wrong results): the A1 rewrite leaves the M1 -> M1 cycle */
+                    if (wa[0] == 0x12345678u && wb[4] == 0x9abcdef0u)
+#endif
+                    {
                     tmem_st4(dst + 5 * SA, wa[0], wa[1], wa[2], wa[3]);
                     if (SB == SA + 1) {
                         tmem_st2(dst + 5 * SA + 4, wa[4], wb[0]);
@@ -657,9 +774,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                         tmem_st4(dst + 5 * SB, wb[0], wb[1], wb[2], wb[3]);
                         tmem_st1(dst + 5 * SB + 4, wb[4]);
                     }
+                    }
                 }
                 tmem_wait_st();
                 tc_fence_before();
+                TL(2, it, t == 0);
 #if SRCNN_PI
                 asm volatile("bar.sync 3, 128;" ::: "memory");       /* all four lane quarters of A1[b] are written */
                 if (warp == W_IM2COL) {
@@ -722,6 +841,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         }
 #else
         const uint32_t b = (uint32_t)(warp - W_E1) >> 2;
+        const bool lead = (uint32_t)(warp & 3) == ((SRCNN_LEADS >> (4 + 4 * b)) & 15u);
         const int total = total_rows(p, span);
         const uint32_t d1 = lane_base + D1_COL + b * D1_STR, a2 = lane_base + A2_COL + b * A2_STR;
 #if SRCNN_PI
@@ -734,21 +854,32 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         for (int g = 0; g < total; g += 2) {
             const uint32_t ph = (g >> 1) & 1;
             uint32_t v[64];
-            WAITS(3, 0, BAR(M1_DONE) + 8u * b, ph);
+            GWAITS(lead, NB_E1 + b, 3, 0, BAR(M1_DONE) + 8u * b, ph);
             tc_fence_after();
+            TL(5, g + b, ((warp & 3) | lane) == 0);
+#ifdef SRCNN_DIAG_D1EARLY   /* timing diagnosis only (races): the D1 drain leaves the M1 -> M1 cycle */
+            warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);
+#endif
             tmem_ld32(d1, v);
             tmem_ld32(d1 + 32, v + 32);
             tmem_wait_ld();
             tc_fence_before();
+            TL(6, g + b, ((warp & 3) | lane) == 0);
+#ifndef SRCNN_DIAG_D1EARLY
             warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);
+#endif
+#ifndef SRCNN_DIAG_E1NOCVT
             #pragma unroll
             for (int m = 0; m < 32; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
-            WAITS(6, 1, BAR(M2_DONE) + 8u * b, ph ^ 1);              /* MMA2 of the previous row of this parity has consumed A2[b] */
+#endif
+            GWAITS(lead, NB_E1 + b, 6, 1, BAR(M2_DONE) + 8u * b, ph ^ 1);              /* MMA2 of the previous row of this parity has consumed A2[b] */
             tc_fence_after();
+            TL(7, g + b, ((warp & 3) | lane) == 0);
             tmem_st16(a2, v);
             tmem_st16(a2 + 16, v + 16);
             tmem_wait_st();
             tc_fence_before();
+            TL(8, g + b, ((warp & 3) | lane) == 0);
 #if SRCNN_PI
             if (b == 0) asm volatile("bar.sync 4, 128;" ::: "memory"); else asm volatile("bar.sync 5, 128;" ::: "memory");
             if (((warp - W_E1) & 3) == 0) {
@@ -780,6 +911,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         reg_dec<64>();
 #endif
         uint32_t kg = 0;                                               /* global pair counter */
+        const bool lead = (warp & 3) == ((SRCNN_LEADS >> 12) & 15);
 #if SRCNN_PI
         uint32_t sgc = 0;                                              /* global conv III set counter */
         const uint32_t db3 = (uint32_t)umma_desc(sW + W_B3, 128, 256);
@@ -820,27 +952,33 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 #pragma unroll
                 for (uint32_t b = 0; b < 2; b++) {
                     uint32_t v[32];
-                    WAITS(7, 0, BAR(M2_DONE + b), ph);
+                    GWAITS(lead, NB_E2, 7, 0, BAR(M2_DONE + b), ph);
                     tc_fence_after();
+                    TL(11, 2 * kg + b, ((warp & 3) | lane) == 0);
                     tmem_ld32(lane_base + D2_COL + b * D2_STR, v);
                     tmem_wait_ld();
                     tc_fence_before();
+                    TL(12, 2 * kg + b, ((warp & 3) | lane) == 0);
                     warp_arrive(BAR(D2_EMPTY + b), lane);
                     if (SRCNN_BIAS2_EPI == 1) {
                         #pragma unroll
                         for (int m = 0; m < 32; m++) v[m] = __float_as_uint(__fadd_rn(__uint_as_float(v[m]), cBias2[m]));
                     }
+#ifndef SRCNN_DIAG_E2NOCVT
                     #pragma unroll
                     for (int m = 0; m < 16; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
+#endif
                     if (b == 0) {
-                        WAITP(1, BAR(A3_EMPTY) + 8u * js, ((kg >> 2) & 1) ^ 1);   /* every set that read this pair slot is done */
+                        GWAITP(lead, NB_E2, 1, BAR(A3_EMPTY) + 8u * js, ((kg >> 2) & 1) ^ 1);   /* every set that read this pair slot is done */
                         tc_fence_after();
                     }
                     tmem_st16(a3 + b * A3_SLOT, v);
+                    TL(13, 2 * kg + b, ((warp & 3) | lane) == 0);
                 }
 #endif
                 tmem_wait_st();
                 tc_fence_before();
+                TL(21, 2 * kg, ((warp & 3) | lane) == 0);
 #if SRCNN_PI
                 asm volatile("bar.sync 6, 128;" ::: "memory");       /* the pair is complete in all four lane quarters */
                 if (warp == W_E2 && k >= 2) {
@@ -895,6 +1033,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         /* ===================== conv III gather: dx across lanes, bias, clamp, store (two rows per set) ======== */
         reg_dec<64>();
         const int t = (warp - W_E3) * 32 + lane;
+        const bool lead = (warp & 3) == ((SRCNN_LEADS >> 16) & 15);
         uint32_t sg = 0;
         for (int u = 0; u < span.nunits; u++) {
             const Unit un = unit_of(p, span, u);
@@ -936,18 +1075,24 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 /* chroma of this pair was requested one set ago; request the next pair's now (a full set period to land) */
                 const float cb0 = ncb0, cr0 = ncr0, al0 = nal0, cb1 = ncb1, cr1 = ncr1, al1 = nal1;
                 if (pp + 1 < un.npairs) load_chroma(r + 2);
-                WAITS(10, 0, BAR(M3_DONE + (sg & 1)), (sg >> 1) & 1);
+                GWAITS(lead, NB_G, 10, 0, BAR(M3_DONE + (sg & 1)), (sg >> 1) & 1);
                 tc_fence_after();
+                TL(17, 2 * sg + 4, t == 0);
                 tmem_ld16(lane_base + D3_COL + (sg & 1) * D3_STR, z);
                 tmem_wait_ld();
                 tc_fence_before();
+                TL(18, 2 * sg + 4, t == 0);
                 warp_arrive(BAR(D3_EMPTY + (sg & 1)), lane);
+#ifdef SRCNN_DIAG_NOGATHER     /* timing diagnosis only (no output) */
+                if (z[0] != 0x12345678u) continue;
+#endif
                 const uint32_t poff = (sg & 1) * (10 * 128 * 4);            /* exchange buffer of this set */
                 const uint32_t pdst = pst + poff;
                 #pragma unroll
                 for (int m = 0; m < 10; m++)
                     asm volatile("st.shared.b32 [%0], %1;" :: "r"(pdst + 512u * m), "r"(z[m]) : "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                TL(19, 2 * sg + 4, t == 0);
                 if (writer) {
                     float o0 = cBias3, o1 = cBias3;
                     #pragma unroll
@@ -993,6 +1138,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                         if (two) reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(g0) + (size_t)p.dw * 3)[t] = w0[96 + t];
                     }
                 }
+                TL(20, 2 * sg + 4, t == 0);
             }
         }
     }
@@ -1126,6 +1272,12 @@ int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, u
     if (!d_prof) cudaMalloc(&d_prof, NWARPS * 4 * 8);
     p.prof = d_prof;
 #endif
+#ifdef SRCNN_TL
+    static long long* d_tl = nullptr;
+    if (!d_tl) cudaMalloc(&d_tl, TL_N * TL_W * 8);
+    cudaMemsetAsync(d_tl, 0, TL_N * TL_W * 8, s);
+    p.prof = d_tl;
+#endif
     if (p.rgb) conv_tc_kernel<true><<<grid, NWARPS * 32, SMEM_BYTES, s>>>(p, map);
     else       launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(NWARPS * 32), SMEM_BYTES, s, p, map);
 #ifdef SRCNN_PROF
@@ -1138,6 +1290,22 @@ int launch_conv_tc(ConvTcState* st, const __half* y16, Y16Geom g, unsigned dw, u
         for (int w = 0; w < NWARPS; w += (w >= W_CTL ? 1 : 4))
             fprintf(stderr, "PROF %-8s total %8lld  wait0 %5.1f%%  wait1 %5.1f%%\n", w >= W_CTL ? ctl[w - W_CTL] : role[w / 4], h[w * 4],
                     100.0 * h[w * 4 + 1] / h[w * 4], 100.0 * h[w * 4 + 2] / h[w * 4]);
+    }
+#endif
+#ifdef SRCNN_TL
+    if (const char* path = getenv("SRCNN_TL_DUMP")) {
+        /* every launch overwrites the dump: the file holds the last (warm) launch */
+        cudaStreamSynchronize(s);
+        std::vector<long long> h(TL_N * TL_W);
+        cudaMemcpy(h.data(), d_tl, h.size() * 8, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(path, "w")) {
+            for (int r = 0; r < TL_N; r++) {
+                fprintf(f, "%d", TL_R0 + r);
+                for (int e = 0; e < TL_W; e++) fprintf(f, " %lld", h[r * TL_W + e]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
     }
 #endif
     cudaError_t e = cudaGetLastError();
