@@ -14,6 +14,7 @@
  */
 #include "kernels.h"
 #include <atomic>
+#include <mutex>
 #include "srcnn_weights_data.h"
 
 namespace srcnn {
@@ -37,76 +38,104 @@ int conv_exact_init()
     return 0;
 }
 
-constexpr int TILE = 16;
-constexpr int POS  = TILE + 4;          /* 20: conv II positions per tile edge */
-constexpr int YT   = TILE + 12;         /* 28: Y samples per tile edge         */
-constexpr int L2P  = POS * POS + 1;     /* channel pitch in shared memory (odd -> no bank conflicts) */
+/* Tile = 28 x 12 outputs: conv I / II are needed at the 32 x 16 = 512 in-image positions around it (conv III's +-2), one position
+ * per thread of a 512-thread CTA.  Round 2: the weights come from SHARED memory as 16-byte broadcast loads and the Y window is
+ * re-read from shared memory per tap instead of living in 81 registers.  ncu on the round-1 kernel (weights as constant-bank
+ * loads through the uniform datapath, 124 registers, 16 warps per SM): 54 % of all stall samples were FMULs waiting for their
+ * LDCU, 17 % the barrier behind a half-empty second pass over 400 positions; issue slots 40 % used.  Now ~64 registers, 32 warps
+ * per SM, no idle lanes.  The arithmetic (order of every sum, separate multiply and add) is unchanged. */
+constexpr int TW_ = 28, TH_ = 12;
+constexpr int PW = TW_ + 4, PH = TH_ + 4;          /* 32 x 16 conv II positions */
+constexpr int YW = TW_ + 12, YH = TH_ + 12;        /* 40 x 24 Y samples         */
+constexpr int NTHR = PW * PH;                      /* 512 */
+constexpr int L2P = NTHR + 1;                      /* channel pitch of the conv II tile in shared memory */
+constexpr int KB = 8;                              /* conv I filters per step: independent chains of dependent adds */
+constexpr size_t EXACT_SMEM = (size_t)(YW * YH + 32 * L2P + 81 * 64 + 64 * 32) * sizeof(float);
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NTHR, 2)
 conv_exact_kernel(const float* __restrict__ y, int dw, int dh, int win_row0, int win_row1,
-                  float* __restrict__ out, int row0, int row1)
+                  float* __restrict__ out, int row0, int row1, const float* __restrict__ w1g, const float* __restrict__ w2g)
 {
-    extern __shared__ float smem[];
-    float* sY  = smem;                  /* [YT][YT]            */
-    float* sL2 = smem + YT * YT;        /* [32][L2P]           */
+    extern __shared__ __align__(16) float smem[];
+    float* sW1 = smem;                      /* [81][64] */
+    float* sW2 = sW1 + 81 * 64;             /* [64][32] */
+    float* sY  = sW2 + 64 * 32;             /* [YH][YW] */
+    float* sL2 = sY + YW * YH;              /* [32][L2P] */
 
-    const int tx0 = blockIdx.x * TILE, ty0 = row0 + blockIdx.y * TILE;
+    const int tx0 = blockIdx.x * TW_, ty0 = row0 + blockIdx.y * TH_;
     const int tid = threadIdx.x;
 
+    for (int i = tid; i < (81 * 64 + 64 * 32) / 4; i += NTHR)
+        reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(i < 81 * 16 ? w1g : w2g - 81 * 64) + i);
     /* Y tile with the reference's clamp padding: sY[i][j] = Y(clamp(ty0-6+i), clamp(tx0-6+j)) */
-    for (int i = tid; i < YT * YT; i += 256) {
+    for (int i = tid; i < YW * YH; i += NTHR) {
         /* rows past the strip's window only feed outputs past row1, which are discarded: keep the read in bounds */
-        const int r = clampi(clampi(ty0 - 6 + i / YT, 0, dh - 1), win_row0, win_row1 - 1);
-        const int c = clampi(tx0 - 6 + i % YT, 0, dw - 1);
+        const int r = clampi(clampi(ty0 - 6 + i / YW, 0, dh - 1), win_row0, win_row1 - 1);
+        const int c = clampi(tx0 - 6 + i % YW, 0, dw - 1);
         sY[i] = __ldg(y + (size_t)(r - win_row0) * dw + c);
     }
     __syncthreads();
 
-    /* conv I + II at the 20x20 positions (tile +-2); positions outside the image are never read */
-    for (int p = tid; p < POS * POS; p += 256) {
-        const int pr = p / POS, pc = p % POS;
+    /* conv I + II at the 32 x 16 positions (tile +-2); positions outside the image are never read */
+    {
+        const int pr = tid / PW, pc = tid % PW;
         const int gr = ty0 - 2 + pr, gc = tx0 - 2 + pc;
-        if (gr < 0 || gr >= dh || gc < 0 || gc >= dw) continue;
-        float win[81];
-        #pragma unroll
-        for (int i = 0; i < 9; i++)
+        if (gr >= 0 && gr < dh && gc >= 0 && gc < dw) {
+            const uint32_t ywa = (uint32_t)__cvta_generic_to_shared(sY + pr * YW + pc);
+            float acc2[32];
             #pragma unroll
-            for (int j = 0; j < 9; j++) win[i * 9 + j] = sY[(pr + i) * YT + pc + j];
-        float acc2[32];
-        #pragma unroll
-        for (int n = 0; n < 32; n++) acc2[n] = 0.f;
-        /* four conv I filters at a time: each filter's 81-term sum is a serial chain of dependent adds (the reference's order must
-         * be kept), four independent chains hide the add latency; the conv II sums then take the four results in filter order */
-        constexpr int KB = 4;
-        #pragma unroll 1
-        for (int k = 0; k < 64; k += KB) {
-            float t[KB];
-            #pragma unroll
-            for (int j = 0; j < KB; j++) t[j] = 0.f;
-            #pragma unroll
-            for (int tap = 0; tap < 81; tap++)
+            for (int n = 0; n < 32; n++) acc2[n] = 0.f;
+            #pragma unroll 1
+            for (int k = 0; k < 64; k += KB) {
+                /* KB filters at a time: each filter's 81-term sum is a serial chain of dependent adds (the reference's order is
+                 * kept), KB independent chains hide the add latency */
+                float t[KB];
                 #pragma unroll
-                for (int j = 0; j < KB; j++) t[j] = __fadd_rn(t[j], __fmul_rn(cW1[tap][k + j], win[tap]));
-            #pragma unroll
-            for (int j = 0; j < KB; j++) {
-                float u = __fadd_rn(t[j], cB1[k + j]);
-                u = (u >= 0.f) ? u : 0.f;
+                for (int j = 0; j < KB; j++) t[j] = 0.f;
                 #pragma unroll
-                for (int n = 0; n < 32; n++) acc2[n] = __fadd_rn(acc2[n], __fmul_rn(u, cW2[k + j][n]));
+                for (int i = 0; i < 9; i++)
+                    #pragma unroll
+                    for (int jj = 0; jj < 9; jj++) {
+                        float v;          /* (asm volatile: re-read per step -- hoisted out of the k loop the window would cost 81 registers) */
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ywa + 4u * (uint32_t)(i * YW + jj)));
+                        #pragma unroll
+                        for (int q = 0; q < KB / 4; q++) {
+                            const float4 w = *reinterpret_cast<const float4*>(sW1 + (i * 9 + jj) * 64 + k + 4 * q);
+                            t[4 * q + 0] = __fadd_rn(t[4 * q + 0], __fmul_rn(w.x, v));
+                            t[4 * q + 1] = __fadd_rn(t[4 * q + 1], __fmul_rn(w.y, v));
+                            t[4 * q + 2] = __fadd_rn(t[4 * q + 2], __fmul_rn(w.z, v));
+                            t[4 * q + 3] = __fadd_rn(t[4 * q + 3], __fmul_rn(w.w, v));
+                        }
+                    }
+                /* the conv II sums take the KB results in filter order */
+                #pragma unroll
+                for (int j = 0; j < KB; j++) {
+                    float u = __fadd_rn(t[j], cB1[k + j]);
+                    u = (u >= 0.f) ? u : 0.f;
+                    #pragma unroll
+                    for (int n = 0; n < 32; n += 4) {
+                        const float4 w = *reinterpret_cast<const float4*>(sW2 + (k + j) * 32 + n);
+                        acc2[n + 0] = __fadd_rn(acc2[n + 0], __fmul_rn(u, w.x));
+                        acc2[n + 1] = __fadd_rn(acc2[n + 1], __fmul_rn(u, w.y));
+                        acc2[n + 2] = __fadd_rn(acc2[n + 2], __fmul_rn(u, w.z));
+                        acc2[n + 3] = __fadd_rn(acc2[n + 3], __fmul_rn(u, w.w));
+                    }
+                }
             }
-        }
-        #pragma unroll
-        for (int n = 0; n < 32; n++) {
-            float t = __fadd_rn(acc2[n], cB2[n]);
-            sL2[n * L2P + p] = (t >= 0.f) ? t : 0.f;
+            #pragma unroll
+            for (int n = 0; n < 32; n++) {
+                const float t = __fadd_rn(acc2[n], cB2[n]);
+                sL2[n * L2P + tid] = (t >= 0.f) ? t : 0.f;
+            }
         }
     }
     __syncthreads();
 
-    /* conv III: one output per thread */
-    const int orow = ty0 + tid / TILE, ocol = tx0 + tid % TILE;
+    /* conv III: one output per thread (the first TW_ x TH_ = 336 threads) */
+    if (tid >= TW_ * TH_) return;
+    const int orow = ty0 + tid / TW_, ocol = tx0 + tid % TW_;
     if (orow >= row1 || ocol >= dw) return;
     int pidx[25];
     #pragma unroll
@@ -114,7 +143,7 @@ conv_exact_kernel(const float* __restrict__ y, int dw, int dh, int win_row0, int
         #pragma unroll
         for (int dx = 0; dx < 5; dx++) {
             const int rr = clampi(orow + dy - 2, 0, dh - 1), cc = clampi(ocol + dx - 2, 0, dw - 1);
-            pidx[dy * 5 + dx] = (rr - (ty0 - 2)) * POS + (cc - (tx0 - 2));
+            pidx[dy * 5 + dx] = (rr - (ty0 - 2)) * PW + (cc - (tx0 - 2));
         }
     float t = 0.f;
     #pragma unroll 1
@@ -134,16 +163,29 @@ conv_exact_kernel(const float* __restrict__ y, int dw, int dh, int win_row0, int
 void launch_conv_exact(const float* y, unsigned dw, unsigned dh, unsigned win_row0, unsigned win_rows,
                        float* out, unsigned row0, unsigned row1, cudaStream_t s)
 {
-    const size_t smem = (size_t)(YT * YT + 32 * L2P) * sizeof(float);
-    /* the opt-in is a per-device function attribute: set it once per device, not on every launch */
+    /* the opt-in and the global copy of the conv I / II weights are per device: set up once per device, not on every launch */
     static std::atomic<bool> configured[64];
+    static float* d_w[64];
+    static std::mutex mu;
     int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !configured[dev].load(std::memory_order_acquire)) {
-        if (cudaFuncSetAttribute(conv_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if (!configured[dev].load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!configured[dev].load(std::memory_order_relaxed)) {
+            float* w = nullptr;
+            if (cudaMalloc(&w, (81 * 64 + 64 * 32) * sizeof(float)) != cudaSuccess) return;
+            if (cudaMemcpy(w, SRCNN_W1, sizeof(SRCNN_W1), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(w + 81 * 64, SRCNN_W2, sizeof(SRCNN_W2), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaFuncSetAttribute(conv_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXACT_SMEM) != cudaSuccess) {
+                cudaFree(w); return;
+            }
+            d_w[dev] = w;
             configured[dev].store(true, std::memory_order_release);
+        }
     }
-    dim3 grid((dw + TILE - 1) / TILE, (row1 - row0 + TILE - 1) / TILE);
-    conv_exact_kernel<<<grid, 256, smem, s>>>(y, (int)dw, (int)dh, (int)win_row0, (int)(win_row0 + win_rows), out, (int)row0, (int)row1);
+    dim3 grid((dw + TW_ - 1) / TW_, (row1 - row0 + TH_ - 1) / TH_);
+    conv_exact_kernel<<<grid, NTHR, EXACT_SMEM, s>>>(y, (int)dw, (int)dh, (int)win_row0, (int)(win_row0 + win_rows), out, (int)row0, (int)row1,
+                                                      d_w[dev], d_w[dev] + 81 * 64);
 }
 
 } // namespace srcnn
