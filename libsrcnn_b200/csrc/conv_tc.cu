@@ -321,10 +321,20 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 /* one lane per warp signals for the whole warp (barrier counts are 4 = warps per group) */
+/* SRCNN_ARRIVE_ALL = 1: every lane arrives for itself (barrier counts x 32): no __syncwarp and no predicated single-lane
+ * arrive on the hand-over path */
+#ifndef SRCNN_ARRIVE_ALL
+#define SRCNN_ARRIVE_ALL 0
+#endif
+constexpr uint32_t ARV = SRCNN_ARRIVE_ALL ? 32u : 1u;      /* arrivals per warp */
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane)
 {
+#if SRCNN_ARRIVE_ALL
+    mbar_arrive(bar);
+#else
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
+#endif
 }
 
 /* ---------------------------------------------------------------- the kernel */
@@ -366,6 +376,13 @@ constexpr int TL_R0 = 96, TL_N = 128, TL_W = 128;      /* per row: 32 events x 4
 #ifndef SRCNN_GWAIT
 #define SRCNN_GWAIT 0
 #endif
+/* SRCNN_PRESLEEP = ns: groups whose next wait is known to be long (epilogue I after its hand-over: the next row of its parity is
+ * two row periods away; gather after a pair; the TMA producer) sleep once before they start polling -- less polling traffic on
+ * the barrier unit without a longer wake-up, as long as the sleep is shorter than the wait */
+#ifndef SRCNN_PRESLEEP
+#define SRCNN_PRESLEEP 0
+#endif
+__device__ __forceinline__ void presleep() { if (SRCNN_PRESLEEP) asm volatile("nanosleep.u32 %0;" :: "n"(SRCNN_PRESLEEP)); }
 #ifndef SRCNN_LEADS
 #define SRCNN_LEADS 0x10320
 #endif
@@ -457,18 +474,18 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     for (int i = tid; i < WIMG_BYTES / 16; i += NWARPS * 32)
         reinterpret_cast<uint4*>(sgen + S_W)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
     if (tid == 0) {
-        for (int i = 0; i < NST; i++) { mbar_init(BAR(Y_FULL + i), 1); mbar_init(BAR(Y_EMPTY + i), 4); }
+        for (int i = 0; i < NST; i++) { mbar_init(BAR(Y_FULL + i), 1); mbar_init(BAR(Y_EMPTY + i), 4 * ARV); }
         for (int b = 0; b < 2; b++) {
             /* (SRCNN_PI: the operand-written half of the merged barriers is a bar.sync inside the producer group; only the
              * four drainer warps arrive here) */
             constexpr int e1w = SRCNN_E1_SPLIT ? 8 : 4;               /* epilogue I warps working on one row */
-            mbar_init(BAR(A1_FULL + b), (SRCNN_MERGE_BAR && !SRCNN_PI) ? 4 + e1w : (SRCNN_PI ? e1w : 4)); mbar_init(BAR(M1_DONE + b), 1);
-            mbar_init(BAR(D1_EMPTY_ + b), e1w);
-            mbar_init(BAR(A2_FULL + b), (SRCNN_MERGE_BAR && !SRCNN_PI) ? e1w + 4 : (SRCNN_PI ? 4 : e1w)); mbar_init(BAR(M2_DONE + b), 1);
-            mbar_init(BAR(D2_EMPTY_ + b), 4);
+            mbar_init(BAR(A1_FULL + b), ARV * ((SRCNN_MERGE_BAR && !SRCNN_PI) ? 4 + e1w : (SRCNN_PI ? e1w : 4))); mbar_init(BAR(M1_DONE + b), 1);
+            mbar_init(BAR(D1_EMPTY_ + b), ARV * e1w);
+            mbar_init(BAR(A2_FULL + b), ARV * ((SRCNN_MERGE_BAR && !SRCNN_PI) ? e1w + 4 : (SRCNN_PI ? 4 : e1w))); mbar_init(BAR(M2_DONE + b), 1);
+            mbar_init(BAR(D2_EMPTY_ + b), ARV * 4);
         }
-        for (int j = 0; j < 4; j++) { mbar_init(BAR(A3_FULL + j), 4); mbar_init(BAR(A3_EMPTY + j), 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(BAR(M3_DONE + b), 1); mbar_init(BAR(D3_EMPTY + b), 4); mbar_init(BAR(A1_FREE + b), 1); }
+        for (int j = 0; j < 4; j++) { mbar_init(BAR(A3_FULL + j), 4 * ARV); mbar_init(BAR(A3_EMPTY + j), 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(BAR(M3_DONE + b), 1); mbar_init(BAR(D3_EMPTY + b), 4 * ARV); mbar_init(BAR(A1_FREE + b), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA2) {
@@ -511,7 +528,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 const int nch = (un.nrows + 8 + CH_ROWS - 1) / CH_ROWS;
                 for (int j = 0; j < nch; j++, ck++) {
                     const uint32_t s = ck % NST, k = ck / NST;
-#if SRCNN_GWAIT && !defined(SRCNN_PROF)
+#if (SRCNN_GWAIT || SRCNN_PRESLEEP) && !defined(SRCNN_PROF)
                     mbar_wait_sleep(BAR(Y_EMPTY + s), (k & 1) ^ 1);
 #else
                     WAITP(0, BAR(Y_EMPTY + s), (k & 1) ^ 1);
@@ -898,6 +915,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             }
 #else
             warp_arrive(BAR(A2_FULL) + 8u * b, lane);
+            presleep();
 #endif
         }
 #endif
@@ -1139,6 +1157,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     }
                 }
                 TL(20, 2 * sg + 4, t == 0);
+                presleep();
             }
         }
     }

@@ -40,7 +40,10 @@ namespace srcnn {
 
 namespace {
 
-constexpr int TH = 32, TW = 128, NT = 256, NW = NT / 32;
+#ifndef SRCNN_PREP_TH
+#define SRCNN_PREP_TH 32
+#endif
+constexpr int TH = SRCNN_PREP_TH, TW = 128, NT = 256, NW = NT / 32;
 constexpr int RPT = TH / (NT / TW);        /* destination rows per thread in the horizontal pass */
 
 /* development switch (A/B timing and parity of the two chroma paths) */
