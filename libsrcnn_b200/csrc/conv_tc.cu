@@ -58,7 +58,18 @@ namespace {
 #ifndef SRCNN_ELECT_OUTER
 #define SRCNN_ELECT_OUTER 0     /* measured (round 2): 0.1320 ms vs 0.1280 ms -- 33 instead of 42 instructions per row in the issue loops, and slower */
 #endif
-#if SRCNN_ELECT_OUTER
+/* SRCNN_ONE_LANE = 1: lanes 1..31 of the three issuer warps EXIT right after the register hand-back, so an issuer is a one-thread
+ * warp: no elect, no divergent region, no reconvergence per row (tools/probe/mma_victim.cu: the elect / issue / __syncwarp loop
+ * costs 222 clk per batch on an idle SM, 88 of them between the commit and the reconverged warp; a lane that runs the whole loop
+ * alone issues at the pipe's 192).  Unlike SRCNN_ELECT_OUTER the other lanes are gone instead of parked at a convergence barrier. */
+#ifndef SRCNN_ONE_LANE
+#define SRCNN_ONE_LANE 0
+#endif
+#if SRCNN_ONE_LANE
+#define ISSUER_BEGIN {
+#define ISSUE_LANE() true
+#define ISSUE_SYNC() ((void)0)
+#elif SRCNN_ELECT_OUTER
 #define ISSUER_BEGIN if (elect_one()) {
 #define ISSUE_LANE() true
 #define ISSUE_SYNC() ((void)0)
@@ -518,6 +529,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     if (warp >= W_CTL) {
         /* ============================ control warpgroup: TMA producer + three MMA issuers ==================== */
         reg_dec<48>();                      /* the setmaxnreg pool is what the dec's release: 4096 + 2048 + 2048 regs */
+        if (SRCNN_ONE_LANE && !SRCNN_PI && warp != W_TMA && lane != 0) return;      /* (exited threads do not take part in the final barrier) */
         if (warp == W_TMA) {
             /* Y16 rows of the current unit, 8-row chunks into a 4-stage ring (rows past the plane are zero-filled) */
             uint32_t ck = 0;
@@ -1169,7 +1181,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
 #endif
     tc_fence_before();
     __syncthreads();
-    if (warp == W_MMA2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+    if (warp == (SRCNN_ONE_LANE ? 0 : W_MMA2)) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
 /* element (n, k) of an N x K K-major no-swizzle operand image: 8x8 core matrices of 128 B, K-adjacent ones contiguous */
