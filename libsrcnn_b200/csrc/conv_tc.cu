@@ -380,9 +380,9 @@ constexpr int TL_R0 = 96, TL_N = 128, TL_W = 128;      /* per row: 32 events x 4
 #endif
 /* SRCNN_GWAIT = 1: only ONE warp of a four-warp group polls an mbarrier; its three siblings block in a named barrier until the
  * poller joins them.  mbarrier.try_wait does not really suspend a warp on this part: with or without a suspend-time hint the retry
- * loop (TRYWAIT / NANOSLEEP.SYNCS / PHASECHK / BRA) spins, and ncu's source page showed ~50 M of the kernel's 116 M issued warp
- * instructions in those loops -- 86 % of all issue slots taken, every working warp slowed to ~10 clk per instruction
- * (tools/conv_timeline.py).  bar.sync waits cost no issue slots.  SRCNN_LEADS: which warp of each group polls, one hex digit per
+ * loop (TRYWAIT / NANOSLEEP.SYNCS / PHASECHK / BRA) spins, and ncu's source page attributes ~45 % of the kernel's issued warp
+ * instructions to those loops.  bar.sync waits cost no issue slots.  Measured: 0.1446 vs 0.1282 ms -- the extra hop costs more than
+ * the freed issue slots give (profiles/r2_conv_pipeline_investigation.md).  SRCNN_LEADS: which warp of each group polls, one hex digit per
  * group (gather, epilogue II, epilogue I odd, epilogue I even, im2col) -- spread over the sub-partitions next to the issuers. */
 #ifndef SRCNN_GWAIT
 #define SRCNN_GWAIT 0
