@@ -115,8 +115,21 @@ constexpr int WIMG_BYTES = W_B3 + B3_BYTES;
 
 /* TMEM columns (512 allocated).  D1/D2/A1/A2 are double-buffered by row parity, A3 is a ring of 8 conv II rows
  * (4 pair slots), D3 is double-buffered by set parity (one set per two output rows). */
+/* SRCNN_TRIPLE = 1 (TIMING DIAGNOSIS ONLY, results wrong): conv I's accumulator and operand are TRIPLE-buffered (row mod 3); the
+ * 112 extra columns are taken from the conv III operand ring, whose eight row slots then alias each other.  Answers one question:
+ * what would a third D1 / A1 buffer buy (the period is the reuse cycle of those two buffers)? */
+#ifndef SRCNN_TRIPLE
+#define SRCNN_TRIPLE 0
+#endif
+#if SRCNN_TRIPLE
+constexpr uint32_t D1_COL = 0, A1_COL = 192, D2_COL = 336, A2_COL = 400, A3_COL = 464, D3_COL = 480;
+constexpr uint32_t D1_STR = 64, D2_STR = 32, A1_STR = 48, A2_STR = 32, A3_SLOT = 0, D3_STR = 16;
+constexpr int NB1 = 3;
+#else
 constexpr uint32_t D1_COL = 0, D2_COL = 128, A2_COL = 192, A1_COL = 256, A3_COL = 352, D3_COL = 480;
 constexpr uint32_t D1_STR = 64, D2_STR = 32, A1_STR = 48, A2_STR = 32, A3_SLOT = 16, D3_STR = 16;
+constexpr int NB1 = 2;
+#endif
 /* conv II bias K-step: its A operand is the LAST K-step of the conv I operand, A1[b] columns 40..47 = k 80..95: k = 90, 91
  * are the constant 1.0 inputs (the bias sits at those k in the B image), every other k meets a zero weight there.  The
  * values under the zero weights are Y samples (finite), whichever row im2col has in flight, so the product is exactly 0. */
@@ -155,8 +168,8 @@ constexpr int W_TMA = W_CTL + (SRCNN_CTLPERM & 15), W_MMA1 = W_CTL + ((SRCNN_CTL
 #ifndef SRCNN_MERGE_BAR
 #define SRCNN_MERGE_BAR 1
 #endif
-enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + 2, D1_EMPTY_ = M1_DONE + 2,
-       A2_FULL = D1_EMPTY_ + 2, M2_DONE = A2_FULL + 2, D2_EMPTY_ = M2_DONE + 2,
+enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + NB1, D1_EMPTY_ = M1_DONE + NB1,
+       A2_FULL = D1_EMPTY_ + NB1, M2_DONE = A2_FULL + 2, D2_EMPTY_ = M2_DONE + 2,
        A3_FULL = D2_EMPTY_ + 2, A3_EMPTY = A3_FULL + 4, M3_DONE = A3_EMPTY + 4, D3_EMPTY = M3_DONE + 2, A1_FREE = D3_EMPTY + 2,
        NBAR = A1_FREE + 2,
        D1_EMPTY = SRCNN_MERGE_BAR ? A1_FULL : D1_EMPTY_, D2_EMPTY = SRCNN_MERGE_BAR ? A2_FULL : D2_EMPTY_ };
@@ -495,6 +508,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             mbar_init(BAR(A2_FULL + b), ARV * ((SRCNN_MERGE_BAR && !SRCNN_PI) ? e1w + 4 : (SRCNN_PI ? 4 : e1w))); mbar_init(BAR(M2_DONE + b), 1);
             mbar_init(BAR(D2_EMPTY_ + b), ARV * 4);
         }
+        if (NB1 == 3) { mbar_init(BAR(A1_FULL + 2), ARV * 8); mbar_init(BAR(M1_DONE + 2), 1); mbar_init(BAR(D1_EMPTY_ + 2), ARV * 4); }
         for (int j = 0; j < 4; j++) { mbar_init(BAR(A3_FULL + j), 4 * ARV); mbar_init(BAR(A3_EMPTY + j), 1); }
         for (int b = 0; b < 2; b++) { mbar_init(BAR(M3_DONE + b), 1); mbar_init(BAR(D3_EMPTY + b), 4 * ARV); mbar_init(BAR(A1_FREE + b), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -563,6 +577,29 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             const uint32_t db0 = (uint32_t)umma_desc(sW, 128, (K1 / 8) * 128);
             constexpr uint32_t dh1 = umma_desc_hi((K1 / 8) * 128);
             uint32_t pr = 0;                                               /* global row-pair counter */
+#if SRCNN_TRIPLE
+            uint32_t b3 = 0, ph3 = 0;
+            for (int u = 0; u < span.nunits; u++) {
+                const Unit un = unit_of(p, span, u);
+                uint32_t R = (uint32_t)(un.ra % 9);
+                #pragma unroll 1
+                for (int n = 0; n < un.nrows; n++) {
+                    WAITS(0, 0, BAR(A1_FULL) + 8u * b3, ph3);
+                    tc_fence_after();
+                    if (ISSUE_LANE()) {
+                        const uint32_t db = db0 + R * (B1_BYTES >> 4);
+                        #pragma unroll
+                        for (int s = 0; s < K1 / 16; s++)
+                            umma_ts(tmem + D1_COL + b3 * D1_STR, tmem + A1_COL + b3 * A1_STR + 8 * s, db + 16 * s, dh1, umma_idesc(N1), s > 0);
+                        umma_commit(BAR(M1_DONE) + 8u * b3);
+                    }
+                    ISSUE_SYNC();
+                    R = (R == NROT - 1) ? 0 : R + 1;
+                    if (++b3 == 3) { b3 = 0; ph3 ^= 1; }
+                }
+            }
+            (void)pr; (void)myb;
+#else
             for (int u = 0; u < span.nunits; u++) {
                 const Unit un = unit_of(p, span, u);
                 uint32_t R = (uint32_t)(un.ra % 9);   /* weight-image rotation of conv II row q: (q + 2) mod 9 */
@@ -609,6 +646,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     }
                 }
             }
+#endif
             ISSUER_END
         } else if (warp == W_MMA2 || warp == W_MMA2B) {
             const uint32_t myb = warp == W_MMA2B;
@@ -617,11 +655,12 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             const uint32_t dbb = (uint32_t)umma_desc(sW + W_B2B, 128, 256);
             constexpr uint32_t dh2 = umma_desc_hi((K2 / 8) * 128), dhb = umma_desc_hi(256);
             const int total = total_rows(p, span);
+            uint32_t r3 = 0;                                               /* SRCNN_TRIPLE: row mod 3 = conv I operand buffer (bias inputs) */
             #pragma unroll 1
             for (int g = 0; g < total; g += 2) {
                 const uint32_t ph = (g >> 1) & 1;
                 #pragma unroll
-                for (uint32_t b = 0; b < 2; b++) {
+                for (uint32_t b = 0; b < 2; b++, r3 = (r3 == 2 ? 0 : r3 + 1)) {
                     if (SRCNN_ISSUE_SPLIT && b != myb) continue;
                     if (ISSUE_LANE()) TLI(23, g + b);
                     WAITS(4, 0, BAR(A2_FULL + b), ph);
@@ -636,7 +675,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                         for (int s = 0; s < K2 / 16; s++)
                             umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR + 8 * s, db + 16 * s, dh2, umma_idesc(N2), s > 0);
                         if (!SRCNN_BIAS2_EPI)
-                            umma_ts(tmem + D2_COL + b * D2_STR, tmem + A1_COL + b * A1_STR + ABIAS_OFF, dbb, dhb, umma_idesc(N2), 1);     /* + bias */
+                            umma_ts(tmem + D2_COL + b * D2_STR, tmem + A1_COL + (SRCNN_TRIPLE ? r3 : b) * A1_STR + ABIAS_OFF, dbb, dhb, umma_idesc(N2), 1);     /* + bias */
 #endif
                         umma_commit(BAR(M2_DONE + b));
                         TLI(10, g + b);
@@ -668,7 +707,9 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     if (ISSUE_LANE()) TLI(24, 2 * sg + 4);
                     WAITS(8, 0, BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
                     if (ISSUE_LANE()) TLI(14, 2 * sg + 4);
+#ifndef SRCNN_DIAG_NOD3WAIT
                     WAITS(9, 1, BAR(D3_EMPTY + (sg & 1)), ((sg >> 1) & 1) ^ 1);
+#endif
                     tc_fence_after();
                     if (ISSUE_LANE()) {
                         TLI(15, 2 * sg + 4);
@@ -758,7 +799,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 constexpr int R = decltype(RC)::value;
                 fetch(n + 8, W[(R + 8) % 9]);
                 if (n < 0) return;
+#if SRCNN_TRIPLE
+                const uint32_t b = it % 3u, ph = (it / 3u) & 1;
+#else
                 const uint32_t b = it & 1, ph = (it >> 1) & 1;
+#endif
                 TL(0, it, t == 0);
 #if SRCNN_A1_EARLY && SRCNN_A1_PARTIAL && !SRCNN_PI
                 /* partial rewrite: only the K-steps that read the two oldest window rows of row it-2 must have run */
@@ -770,7 +815,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 tc_fence_after();
                 TL(1, it, t == 0);
                 const uint32_t dst = lane_base + A1_COL + b * A1_STR;
-                if (!SRCNN_A1_PARTIAL || n < 2) {
+                if (!SRCNN_A1_PARTIAL || n < NB1) {
                     /* first two rows of a unit: the whole operand (both parity buffers still hold another unit's rows) */
                     uint32_t r[16];
                     #pragma unroll
@@ -787,6 +832,13 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 } else {
                     /* A1[b] still holds the operand of row n-2, and the slot -> column map never moves: only the two ring
                      * slots refilled since then (Y rows n+7 and n+8) differ -- 10 of the 48 columns */
+#if SRCNN_TRIPLE
+                    {   /* three ring slots changed since the same-buffer row three rows earlier */
+                        constexpr int SZ = (R + 6) % 9;
+                        tmem_st4(dst + 5 * SZ, W[SZ][0], W[SZ][1], W[SZ][2], W[SZ][3]);
+                        tmem_st1(dst + 5 * SZ + 4, W[SZ][4]);
+                    }
+#endif
                     constexpr int SA = (R + 7) % 9, SB = (R + 8) % 9;
                     const uint32_t (&wa)[5] = W[SA];
                     const uint32_t (&wb)[5] = W[SB];
@@ -872,22 +924,38 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         const uint32_t b = (uint32_t)(warp - W_E1) >> 2;
         const bool lead = (uint32_t)(warp & 3) == ((SRCNN_LEADS >> (4 + 4 * b)) & 15u);
         const int total = total_rows(p, span);
-        const uint32_t d1 = lane_base + D1_COL + b * D1_STR, a2 = lane_base + A2_COL + b * A2_STR;
+#if !SRCNN_TRIPLE
+        const uint32_t d1 = lane_base + D1_COL + b * D1_STR;
+#endif
+        const uint32_t a2 = lane_base + A2_COL + b * A2_STR;
 #if SRCNN_PI
         const uint32_t db2 = (uint32_t)umma_desc(sW + W_B2, 128, (K2 / 8) * 128);
         const uint32_t dbb2 = (uint32_t)umma_desc(sW + W_B2B, 128, 256);
         constexpr uint32_t dh2 = umma_desc_hi((K2 / 8) * 128), dhb2 = umma_desc_hi(256);
 #endif
+#if SRCNN_TRIPLE
+        if (total > 0) { warp_arrive(BAR(D1_EMPTY) + 8u * b, lane); if (b == 0) warp_arrive(BAR(D1_EMPTY) + 8u * 2, lane); }
+        uint32_t b3 = b, ph3 = 0;                                        /* buffer and phase of this group's current row g + b */
+#else
         if (SRCNN_MERGE_BAR && total > 0) warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);     /* D1[b] starts out drained */
+#endif
         #pragma unroll 1
         for (int g = 0; g < total; g += 2) {
             const uint32_t ph = (g >> 1) & 1;
             uint32_t v[64];
+#if SRCNN_TRIPLE
+            const uint32_t d1 = lane_base + D1_COL + b3 * D1_STR;
+            const uint32_t bar1 = BAR(M1_DONE) + 8u * b3, bare = BAR(D1_EMPTY) + 8u * b3;
+            GWAITS(lead, NB_E1 + b, 3, 0, bar1, ph3);
+            b3 += 2; if (b3 >= 3) { b3 -= 3; ph3 ^= 1; }
+#else
+            const uint32_t bare = BAR(D1_EMPTY) + 8u * b;
             GWAITS(lead, NB_E1 + b, 3, 0, BAR(M1_DONE) + 8u * b, ph);
+#endif
             tc_fence_after();
             TL(5, g + b, ((warp & 3) | lane) == 0);
 #ifdef SRCNN_DIAG_D1EARLY   /* timing diagnosis only (races): the D1 drain leaves the M1 -> M1 cycle */
-            warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);
+            warp_arrive(bare, lane);
 #endif
             tmem_ld32(d1, v);
             tmem_ld32(d1 + 32, v + 32);
@@ -895,13 +963,15 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             tc_fence_before();
             TL(6, g + b, ((warp & 3) | lane) == 0);
 #ifndef SRCNN_DIAG_D1EARLY
-            warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);
+            warp_arrive(bare, lane);
 #endif
 #ifndef SRCNN_DIAG_E1NOCVT
             #pragma unroll
             for (int m = 0; m < 32; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
 #endif
+#ifndef SRCNN_DIAG_NOM2WAIT
             GWAITS(lead, NB_E1 + b, 6, 1, BAR(M2_DONE) + 8u * b, ph ^ 1);              /* MMA2 of the previous row of this parity has consumed A2[b] */
+#endif
             tc_fence_after();
             TL(7, g + b, ((warp & 3) | lane) == 0);
             tmem_st16(a2, v);
@@ -999,7 +1069,9 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     for (int m = 0; m < 16; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
 #endif
                     if (b == 0) {
+#ifndef SRCNN_DIAG_NOA3WAIT     /* timing diagnosis only (races): is the conv III operand ring's reuse cycle the binding one? */
                         GWAITP(lead, NB_E2, 1, BAR(A3_EMPTY) + 8u * js, ((kg >> 2) & 1) ^ 1);   /* every set that read this pair slot is done */
+#endif
                         tc_fence_after();
                     }
                     tmem_st16(a3 + b * A3_SLOT, v);
