@@ -810,7 +810,9 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 WAITS(2, 1, BAR(A1_FREE) + 8u * b, ph ^ 1);
                 if (n < 2) WAITS(2, 1, BAR(M1_DONE) + 8u * b, ph ^ 1);     /* whole operand rewritten: all of row it-2's MMAs */
 #else
+#ifndef SRCNN_DIAG_NOA1WAIT    /* timing diagnosis only (races): the operand side leaves conv I's reuse cycle altogether */
                 GWAITS(lead, NB_IM, 2, 1, BAR(M1_DONE) + 8u * b, ph ^ 1);         /* MMA1 of row it-2 has consumed A1[b] */
+#endif
 #endif
                 tc_fence_after();
                 TL(1, it, t == 0);
