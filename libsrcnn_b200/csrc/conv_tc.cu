@@ -121,6 +121,14 @@ constexpr int WIMG_BYTES = W_B3 + B3_BYTES;
 #ifndef SRCNN_TRIPLE
 #define SRCNN_TRIPLE 0
 #endif
+/* SRCNN_E1IM = 1: there is no im2col group.  The epilogue I group of a row parity, which drains D1[b] after conv I of row g, also
+ * rewrites the operand A1[b] for row g + 2 (same barrier to wait for, one arrival covers "operand written" and "accumulator
+ * drained"): one station less on the conv I reuse cycle, and the busiest one (the wait profile has im2col outside its waits 80 % of
+ * the time, the two epilogue I groups 37 %).  The Y rows come from the shared-memory ring without a register window: two rows per
+ * partial rewrite, nine for the first row of a unit. */
+#ifndef SRCNN_E1IM
+#define SRCNN_E1IM 0
+#endif
 #if SRCNN_TRIPLE
 constexpr uint32_t D1_COL = 0, A1_COL = 192, D2_COL = 336, A2_COL = 400, A3_COL = 464, D3_COL = 480;
 constexpr uint32_t D1_STR = 64, D2_STR = 32, A1_STR = 48, A2_STR = 32, A3_SLOT = 0, D3_STR = 16;
@@ -475,6 +483,61 @@ __device__ __forceinline__ int total_rows(const TcParams& p, const Span& sp)
 }
 
 
+/* SRCNN_E1IM: cursor of an epilogue I group over the rows whose conv I operand it writes, and its view of the Y16 ring */
+struct E1Cur { int nu, nn, nrows, ra9; uint32_t ckbase, got, rel, woff, sh; };
+__device__ __forceinline__ void e1_enter(E1Cur& c, const Unit& un, uint32_t sY, int t)
+{
+    const int hw = ((un.band * kBandCols + 2) & 7) + t;               /* half offset of this lane's window in the box */
+    c.woff = sY + (uint32_t)(hw >> 1) * 4u; c.sh = (uint32_t)(hw & 1) * 16u;
+    c.nrows = un.nrows; c.ra9 = un.ra % 9;
+}
+/* plane row rho of the cursor's unit -> five words (ten halves) */
+__device__ __forceinline__ void e1_ldrow(E1Cur& c, uint32_t bar0, int rho, uint32_t (&w5)[5])
+{
+    const uint32_t cl = (uint32_t)rho / CH_ROWS;
+    while (c.got <= cl) { const uint32_t k = c.ckbase + c.got; mbar_wait(bar0 + 8u * (Y_FULL + (k % NST)), (k / NST) & 1); c.got++; }
+    const uint32_t k = c.ckbase + cl;
+    const uint32_t a = c.woff + (k % NST) * CH_BYTES + ((uint32_t)rho % CH_ROWS) * (BOX_W * 2);
+    uint32_t x[6];
+    #pragma unroll
+    for (int j = 0; j < 6; j++) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[j]) : "r"(a + 4u * j));
+    #pragma unroll
+    for (int j = 0; j < 5; j++) w5[j] = __funnelshift_r(x[j], x[j + 1], c.sh);
+}
+/* whole operand of row (nu, nn): ring slot s holds the plane row rho with (ra + rho) mod 9 == s, rho in nn .. nn+8 */
+__device__ __forceinline__ void e1_write_full(E1Cur& c, uint32_t bar0, uint32_t a1)
+{
+    uint32_t W[9][5];
+    const int base = (c.ra9 + c.nn) % 9;
+    #pragma unroll
+    for (int sl = 0; sl < 9; sl++) e1_ldrow(c, bar0, c.nn + (sl + 9 - base) % 9, W[sl]);
+    uint32_t r[16];
+    #pragma unroll
+    for (int m = 0; m < 16; m++) r[m] = W[m / 5][m % 5];
+    tmem_st16(a1, r);
+    #pragma unroll
+    for (int m = 0; m < 16; m++) r[m] = W[(m + 16) / 5][(m + 16) % 5];
+    tmem_st16(a1 + 16, r);
+    #pragma unroll
+    for (int m = 0; m < 13; m++) r[m] = W[(m + 32) / 5][(m + 32) % 5];
+    r[13] = 0x3C003C00u;                                               /* k = 90, 91: constant 1.0 (bias inputs) */
+    r[14] = 0u; r[15] = 0u;
+    tmem_st16(a1 + 32, r);
+}
+/* after the operand of (nu, nn) has been written: free the ring chunks the next row of this parity does not need, step on */
+__device__ __forceinline__ void e1_advance(E1Cur& c, const TcParams& p, const Span& span, uint32_t bar0, uint32_t sY, int t, int b, int lane)
+{
+    uint32_t upto;
+    const bool last = c.nn + 2 >= c.nrows;
+    if (!last) upto = (uint32_t)(c.nn + 9) / CH_ROWS;                  /* the next row reads plane rows >= nn + 9 */
+    else       upto = (uint32_t)((c.nrows + 8 + CH_ROWS - 1) / CH_ROWS);
+    while (c.rel < upto) { const uint32_t k = c.ckbase + c.rel; warp_arrive(bar0 + 8u * (Y_EMPTY + (k % NST)), lane); c.rel++; }
+    if (!last) { c.nn += 2; return; }
+    c.ckbase += upto; c.got = 0; c.rel = 0;
+    c.nu++; c.nn = b;
+    if (c.nu < span.nunits) e1_enter(c, unit_of(p, span, c.nu), sY, t);
+}
+
 /* FUSE: the gather group's store stage also does colour-out (optional, measured slower); the default instantiation
  * carries none of that code */
 template <bool FUSE>
@@ -498,12 +561,12 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     for (int i = tid; i < WIMG_BYTES / 16; i += NWARPS * 32)
         reinterpret_cast<uint4*>(sgen + S_W)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
     if (tid == 0) {
-        for (int i = 0; i < NST; i++) { mbar_init(BAR(Y_FULL + i), 1); mbar_init(BAR(Y_EMPTY + i), 4 * ARV); }
+        for (int i = 0; i < NST; i++) { mbar_init(BAR(Y_FULL + i), 1); mbar_init(BAR(Y_EMPTY + i), (SRCNN_E1IM ? 8 : 4) * ARV); }
         for (int b = 0; b < 2; b++) {
             /* (SRCNN_PI: the operand-written half of the merged barriers is a bar.sync inside the producer group; only the
              * four drainer warps arrive here) */
             constexpr int e1w = SRCNN_E1_SPLIT ? 8 : 4;               /* epilogue I warps working on one row */
-            mbar_init(BAR(A1_FULL + b), ARV * ((SRCNN_MERGE_BAR && !SRCNN_PI) ? 4 + e1w : (SRCNN_PI ? e1w : 4))); mbar_init(BAR(M1_DONE + b), 1);
+            mbar_init(BAR(A1_FULL + b), ARV * (SRCNN_E1IM ? 4 : (SRCNN_MERGE_BAR && !SRCNN_PI) ? 4 + e1w : (SRCNN_PI ? e1w : 4))); mbar_init(BAR(M1_DONE + b), 1);
             mbar_init(BAR(D1_EMPTY_ + b), ARV * e1w);
             mbar_init(BAR(A2_FULL + b), ARV * ((SRCNN_MERGE_BAR && !SRCNN_PI) ? e1w + 4 : (SRCNN_PI ? 4 : e1w))); mbar_init(BAR(M2_DONE + b), 1);
             mbar_init(BAR(D2_EMPTY_ + b), ARV * 4);
@@ -758,6 +821,73 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             }
             ISSUER_END
         }
+#if SRCNN_E1IM
+    } else if (warp >= W_IM2COL && warp < W_IM2COL + 4) {
+        reg_dec<24>();                      /* (idle: its registers go to the epilogue I groups) */
+    } else if (warp >= W_E1 && warp < W_E1 + 8) {
+        /* ===================== epilogue I + operand rewrite (two groups, one per row parity) ================== */
+        reg_inc<120>();
+        const uint32_t b = (uint32_t)(warp - W_E1) >> 2;
+        const int t = ((warp - W_E1) & 3) * 32 + lane;
+        const uint32_t d1 = lane_base + D1_COL + b * D1_STR, a2 = lane_base + A2_COL + b * A2_STR, a1 = lane_base + A1_COL + b * A1_STR;
+        const int total = total_rows(p, span);
+        /* cursor over the rows of this parity whose operand is written next: unit nu, row nn (nn = b, b+2, ...); everything the
+         * cursor needs lives in plain scalars (the helpers are force-inlined: no closure object in local memory) */
+        E1Cur cu;
+        cu.nu = 0; cu.nn = (int)b; cu.ckbase = 0; cu.got = 0; cu.rel = 0; cu.nrows = 0; cu.ra9 = 0; cu.woff = 0; cu.sh = 0;
+        if (span.nunits > 0) e1_enter(cu, unit_of(p, span, 0), sY, t);
+        if (total > 0) {
+            /* prologue: the operand of this parity's first row; D1[b] starts out drained */
+            e1_write_full(cu, bar0, a1);
+            tmem_wait_st();
+            tc_fence_before();
+            warp_arrive(BAR(A1_FULL) + 8u * b, lane);
+            e1_advance(cu, p, span, bar0, sY, t, (int)b, lane);
+        }
+        #pragma unroll 1
+        for (int g = 0; g < total; g += 2) {
+            const uint32_t ph = (g >> 1) & 1;
+            const bool more = cu.nu < span.nunits;                     /* an operand is still to be written (row g + 2 of this parity) */
+            const bool full = more && cu.nn < 2;
+            uint32_t wa[5], wb[5];
+            uint32_t sa = 0;
+            if (more && !full) {                                       /* the two new plane rows, fetched before the wait */
+                e1_ldrow(cu, bar0, cu.nn + 7, wa); e1_ldrow(cu, bar0, cu.nn + 8, wb);
+                sa = (uint32_t)(cu.ra9 + cu.nn + 7) % 9u;
+            }
+            WAITP(0, BAR(M1_DONE) + 8u * b, ph);
+            tc_fence_after();
+            uint32_t v[64];
+            if (!full) { tmem_ld32(d1, v); tmem_ld32(d1 + 32, v + 32); }
+            if (more) {
+                if (full) { e1_write_full(cu, bar0, a1); tmem_ld32(d1, v); tmem_ld32(d1 + 32, v + 32); }
+                else if (sa != 8u) {                                   /* ten adjacent columns */
+                    tmem_st4(a1 + 5 * sa, wa[0], wa[1], wa[2], wa[3]);
+                    tmem_st2(a1 + 5 * sa + 4, wa[4], wb[0]);
+                    tmem_st4(a1 + 5 * sa + 6, wb[1], wb[2], wb[3], wb[4]);
+                } else {                                               /* slots 8 and 0 */
+                    tmem_st4(a1 + 40, wa[0], wa[1], wa[2], wa[3]);
+                    tmem_st1(a1 + 44, wa[4]);
+                    tmem_st4(a1, wb[0], wb[1], wb[2], wb[3]);
+                    tmem_st1(a1 + 4, wb[4]);
+                }
+                tmem_wait_st();
+            }
+            tmem_wait_ld();
+            tc_fence_before();
+            warp_arrive(BAR(A1_FULL) + 8u * b, lane);                  /* operand of row g + 2 written, accumulator of row g drained */
+            #pragma unroll
+            for (int m = 0; m < 32; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
+            WAITP(1, BAR(M2_DONE) + 8u * b, ph ^ 1);                   /* MMA2 of the previous row of this parity has consumed A2[b] */
+            tc_fence_after();
+            tmem_st16(a2, v);
+            tmem_st16(a2 + 16, v + 16);
+            tmem_wait_st();
+            tc_fence_before();
+            warp_arrive(BAR(A2_FULL) + 8u * b, lane);
+            if (more) e1_advance(cu, p, span, bar0, sY, t, (int)b, lane);       /* (off the hand-over paths) */
+        }
+#else
     } else if (warp >= W_IM2COL && warp < W_IM2COL + 4) {
         /* ===================== im2col: smem Y16 ring -> 9-slot register ring -> A1 in TMEM ==================== */
         reg_inc<96>();
@@ -1003,6 +1133,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
 #endif
         }
 #endif
+#endif   /* SRCNN_E1IM */
     } else if (warp >= W_E2 && warp < W_E2 + 4) {
         /* ===================== epilogue II: D2 (bias included) -> ReLU -> FP16 -> A3 ring ===================== */
 #if SRCNN_E2_DECOUPLE

@@ -5,7 +5,7 @@ out=$1; shift; mkdir -p $out
 for v in "$@" ; do
   n=${v#+}
   if [ "$v" != "$n" ]; then
-    SRCNN_B200_LIB=ab/lib_$n.so timeout 600 python -m pytest tests/test_parity_gpu.py -x -q -m gpu -k "conv_tensor or strips or frame_groups or batch or c2_full or butterfly" 2>&1 | tail -3 | sed "s/^/[$n] /" >> $out/log.txt
+    SRCNN_B200_LIB=ab/lib_$n.so timeout ${PTMO:-600} python -m pytest tests/test_parity_gpu.py -x -q -m gpu -k "conv_tensor or strips or frame_groups or batch or c2_full or butterfly" 2>&1 | tail -3 | sed "s/^/[$n] /" >> $out/log.txt
   fi
   for rep in ${REPS:-1 2}; do
     SRCNN_B200_LIB=ab/lib_$n.so timeout ${TMO:-45} python tools/conv_time.py 30 2>&1 | tail -1 >> $out/log.txt || echo "$n: FAILED/TIMEOUT" >> $out/log.txt
