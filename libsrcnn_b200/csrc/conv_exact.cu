@@ -49,7 +49,10 @@ constexpr int PW = TW_ + 4, PH = TH_ + 4;          /* 32 x 16 conv II positions 
 constexpr int YW = TW_ + 12, YH = TH_ + 12;        /* 40 x 24 Y samples         */
 constexpr int NTHR = PW * PH;                      /* 512 */
 constexpr int L2P = NTHR + 1;                      /* channel pitch of the conv II tile in shared memory */
-constexpr int KB = 8;                              /* conv I filters per step: independent chains of dependent adds */
+#ifndef SRCNN_EXACT_KB
+#define SRCNN_EXACT_KB 16     /* measured: 4 -> 2.339 ms, 8 -> 2.244 ms, 16 -> 2.201 ms per 1920x1080 pass */
+#endif
+constexpr int KB = SRCNN_EXACT_KB;                              /* conv I filters per step: independent chains of dependent adds */
 constexpr size_t EXACT_SMEM = (size_t)(YW * YH + 32 * L2P + 81 * 64 + 64 * 32) * sizeof(float);
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
