@@ -35,17 +35,19 @@ __device__ __forceinline__ void group(uint32_t d, uint32_t a, uint64_t db)
     for (int s = 0; s < KS; s++) mma_ts(d, a + 8 * (s & 1), db + 16 * (s & 3), idesc_of(N), s > 0);
 }
 
-template <int MODE>
+template <int MODE, int COMMIT>
 __global__ void __launch_bounds__(160) k(int iters, long long* out)
 {
     __shared__ __align__(128) unsigned char sB[256 * 16 * 2 * 4];
     __shared__ __align__(8) uint64_t bar[3];
+    __shared__ __align__(8) uint64_t cbar[3];     /* COMMIT = 1: a tcgen05.commit after every group (as the conv kernel does), never waited for */
     __shared__ uint32_t s_tmem;
     __shared__ volatile int ticket;
     const int t = threadIdx.x, warp = t >> 5;
     for (int i = t; i < (int)sizeof(sB) / 4; i += blockDim.x) ((uint32_t*)sB)[i] = 0;
     if (t == 0) {
         for (int i = 0; i < 3; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar[i])));
+        for (int i = 0; i < 3; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&cbar[i])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         ticket = 0;
     }
@@ -66,8 +68,11 @@ __global__ void __launch_bounds__(160) k(int iters, long long* out)
             #pragma unroll 1
             for (int it = 0; it < iters; it++) {
                 group<64, 6>(tmem + (it & 1) * 64, A, db);
+                if (COMMIT) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&cbar[0])) : "memory");
                 group<32, 5>(tmem + 128 + (it & 1) * 32, A, db);
+                if (COMMIT) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&cbar[1])) : "memory");
                 group<16, 6>(tmem + 192, A, db);
+                if (COMMIT) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&cbar[2])) : "memory");
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar[0])) : "memory");
             mbar_wait(smem_u32(&bar[0]), 0);
@@ -82,6 +87,7 @@ __global__ void __launch_bounds__(160) k(int iters, long long* out)
                 if (w == 0) group<64, 6>(tmem + (it & 1) * 64, A, db);
                 else if (w == 1) group<32, 5>(tmem + 128 + (it & 1) * 32, A, db);
                 else group<16, 6>(tmem + 192, A, db);
+                if (COMMIT) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&cbar[w])) : "memory");
                 if (MODE == 2) { __threadfence_block(); ticket = 3 * it + w + 1; }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar[w])) : "memory");
@@ -95,11 +101,11 @@ __global__ void __launch_bounds__(160) k(int iters, long long* out)
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
-template <int MODE> void run(const char* name)
+template <int MODE, int COMMIT = 0> void run(const char* name)
 {
     long long* d; cudaMalloc(&d, 3 * 148 * 8); cudaMemset(d, 0, 3 * 148 * 8);
     const int iters = 4000;
-    k<MODE><<<148, 160>>>(iters, d);
+    k<MODE, COMMIT><<<148, 160>>>(iters, d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[3 * 148]; cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
     long long mx = 0; for (int i = 0; i < 3 * 148; i++) mx = h[i] > mx ? h[i] : mx;
@@ -113,5 +119,7 @@ int main()
     run<2>("three issuers, ticket lock per group");
     run<0>("one issuer, groups back to back");
     run<1>("three issuers, unordered");
+    run<0, 1>("one issuer, a commit after every group");
+    run<1, 1>("three issuers, a commit after every group");
     return 0;
 }
