@@ -115,29 +115,11 @@ constexpr int WIMG_BYTES = W_B3 + B3_BYTES;
 
 /* TMEM columns (512 allocated).  D1/D2/A1/A2 are double-buffered by row parity, A3 is a ring of 8 conv II rows
  * (4 pair slots), D3 is double-buffered by set parity (one set per two output rows). */
-/* SRCNN_TRIPLE = 1 (TIMING DIAGNOSIS ONLY, results wrong): conv I's accumulator and operand are TRIPLE-buffered (row mod 3); the
- * 112 extra columns are taken from the conv III operand ring, whose eight row slots then alias each other.  Answers one question:
- * what would a third D1 / A1 buffer buy (the period is the reuse cycle of those two buffers)? */
-#ifndef SRCNN_TRIPLE
-#define SRCNN_TRIPLE 0
-#endif
-/* SRCNN_E1IM = 1: there is no im2col group.  The epilogue I group of a row parity, which drains D1[b] after conv I of row g, also
- * rewrites the operand A1[b] for row g + 2 (same barrier to wait for, one arrival covers "operand written" and "accumulator
- * drained"): one station less on the conv I reuse cycle, and the busiest one (the wait profile has im2col outside its waits 80 % of
- * the time, the two epilogue I groups 37 %).  The Y rows come from the shared-memory ring without a register window: two rows per
- * partial rewrite, nine for the first row of a unit. */
-#ifndef SRCNN_E1IM
-#define SRCNN_E1IM 0
-#endif
-#if SRCNN_TRIPLE
-constexpr uint32_t D1_COL = 0, A1_COL = 192, D2_COL = 336, A2_COL = 400, A3_COL = 464, D3_COL = 480;
-constexpr uint32_t D1_STR = 64, D2_STR = 32, A1_STR = 48, A2_STR = 32, A3_SLOT = 0, D3_STR = 16;
-constexpr int NB1 = 3;
-#else
+/* (Measured and removed again, see profiles/r2_conv_pipeline_investigation.md and commit eb98414: a timing-only build with
+ * triple-buffered D1 / A1 -- 0.1402 vs 0.1349 ms --, timing-only builds without single stages or waits, and SRCNN_E1IM, the
+ * epilogue I groups doing im2col's operand rewrite as well -- bit-identical, 0.2246 vs 0.1334 ms.) */
 constexpr uint32_t D1_COL = 0, D2_COL = 128, A2_COL = 192, A1_COL = 256, A3_COL = 352, D3_COL = 480;
 constexpr uint32_t D1_STR = 64, D2_STR = 32, A1_STR = 48, A2_STR = 32, A3_SLOT = 16, D3_STR = 16;
-constexpr int NB1 = 2;
-#endif
 /* conv II bias K-step: its A operand is the LAST K-step of the conv I operand, A1[b] columns 40..47 = k 80..95: k = 90, 91
  * are the constant 1.0 inputs (the bias sits at those k in the B image), every other k meets a zero weight there.  The
  * values under the zero weights are Y samples (finite), whichever row im2col has in flight, so the product is exactly 0. */
@@ -176,8 +158,8 @@ constexpr int W_TMA = W_CTL + (SRCNN_CTLPERM & 15), W_MMA1 = W_CTL + ((SRCNN_CTL
 #ifndef SRCNN_MERGE_BAR
 #define SRCNN_MERGE_BAR 1
 #endif
-enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + NB1, D1_EMPTY_ = M1_DONE + NB1,
-       A2_FULL = D1_EMPTY_ + NB1, M2_DONE = A2_FULL + 2, D2_EMPTY_ = M2_DONE + 2,
+enum { Y_FULL = 0, Y_EMPTY = NST, A1_FULL = 2 * NST, M1_DONE = A1_FULL + 2, D1_EMPTY_ = M1_DONE + 2,
+       A2_FULL = D1_EMPTY_ + 2, M2_DONE = A2_FULL + 2, D2_EMPTY_ = M2_DONE + 2,
        A3_FULL = D2_EMPTY_ + 2, A3_EMPTY = A3_FULL + 4, M3_DONE = A3_EMPTY + 4, D3_EMPTY = M3_DONE + 2, A1_FREE = D3_EMPTY + 2,
        NBAR = A1_FREE + 2,
        D1_EMPTY = SRCNN_MERGE_BAR ? A1_FULL : D1_EMPTY_, D2_EMPTY = SRCNN_MERGE_BAR ? A2_FULL : D2_EMPTY_ };
@@ -483,61 +465,6 @@ __device__ __forceinline__ int total_rows(const TcParams& p, const Span& sp)
 }
 
 
-/* SRCNN_E1IM: cursor of an epilogue I group over the rows whose conv I operand it writes, and its view of the Y16 ring */
-struct E1Cur { int nu, nn, nrows, ra9; uint32_t ckbase, got, rel, woff, sh; };
-__device__ __forceinline__ void e1_enter(E1Cur& c, const Unit& un, uint32_t sY, int t)
-{
-    const int hw = ((un.band * kBandCols + 2) & 7) + t;               /* half offset of this lane's window in the box */
-    c.woff = sY + (uint32_t)(hw >> 1) * 4u; c.sh = (uint32_t)(hw & 1) * 16u;
-    c.nrows = un.nrows; c.ra9 = un.ra % 9;
-}
-/* plane row rho of the cursor's unit -> five words (ten halves) */
-__device__ __forceinline__ void e1_ldrow(E1Cur& c, uint32_t bar0, int rho, uint32_t (&w5)[5])
-{
-    const uint32_t cl = (uint32_t)rho / CH_ROWS;
-    while (c.got <= cl) { const uint32_t k = c.ckbase + c.got; mbar_wait(bar0 + 8u * (Y_FULL + (k % NST)), (k / NST) & 1); c.got++; }
-    const uint32_t k = c.ckbase + cl;
-    const uint32_t a = c.woff + (k % NST) * CH_BYTES + ((uint32_t)rho % CH_ROWS) * (BOX_W * 2);
-    uint32_t x[6];
-    #pragma unroll
-    for (int j = 0; j < 6; j++) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[j]) : "r"(a + 4u * j));
-    #pragma unroll
-    for (int j = 0; j < 5; j++) w5[j] = __funnelshift_r(x[j], x[j + 1], c.sh);
-}
-/* whole operand of row (nu, nn): ring slot s holds the plane row rho with (ra + rho) mod 9 == s, rho in nn .. nn+8 */
-__device__ __forceinline__ void e1_write_full(E1Cur& c, uint32_t bar0, uint32_t a1)
-{
-    uint32_t W[9][5];
-    const int base = (c.ra9 + c.nn) % 9;
-    #pragma unroll
-    for (int sl = 0; sl < 9; sl++) e1_ldrow(c, bar0, c.nn + (sl + 9 - base) % 9, W[sl]);
-    uint32_t r[16];
-    #pragma unroll
-    for (int m = 0; m < 16; m++) r[m] = W[m / 5][m % 5];
-    tmem_st16(a1, r);
-    #pragma unroll
-    for (int m = 0; m < 16; m++) r[m] = W[(m + 16) / 5][(m + 16) % 5];
-    tmem_st16(a1 + 16, r);
-    #pragma unroll
-    for (int m = 0; m < 13; m++) r[m] = W[(m + 32) / 5][(m + 32) % 5];
-    r[13] = 0x3C003C00u;                                               /* k = 90, 91: constant 1.0 (bias inputs) */
-    r[14] = 0u; r[15] = 0u;
-    tmem_st16(a1 + 32, r);
-}
-/* after the operand of (nu, nn) has been written: free the ring chunks the next row of this parity does not need, step on */
-__device__ __forceinline__ void e1_advance(E1Cur& c, const TcParams& p, const Span& span, uint32_t bar0, uint32_t sY, int t, int b, int lane)
-{
-    uint32_t upto;
-    const bool last = c.nn + 2 >= c.nrows;
-    if (!last) upto = (uint32_t)(c.nn + 9) / CH_ROWS;                  /* the next row reads plane rows >= nn + 9 */
-    else       upto = (uint32_t)((c.nrows + 8 + CH_ROWS - 1) / CH_ROWS);
-    while (c.rel < upto) { const uint32_t k = c.ckbase + c.rel; warp_arrive(bar0 + 8u * (Y_EMPTY + (k % NST)), lane); c.rel++; }
-    if (!last) { c.nn += 2; return; }
-    c.ckbase += upto; c.got = 0; c.rel = 0;
-    c.nu++; c.nn = b;
-    if (c.nu < span.nunits) e1_enter(c, unit_of(p, span, c.nu), sY, t);
-}
-
 /* FUSE: the gather group's store stage also does colour-out (optional, measured slower); the default instantiation
  * carries none of that code */
 template <bool FUSE>
@@ -561,17 +488,16 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
     for (int i = tid; i < WIMG_BYTES / 16; i += NWARPS * 32)
         reinterpret_cast<uint4*>(sgen + S_W)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
     if (tid == 0) {
-        for (int i = 0; i < NST; i++) { mbar_init(BAR(Y_FULL + i), 1); mbar_init(BAR(Y_EMPTY + i), (SRCNN_E1IM ? 8 : 4) * ARV); }
+        for (int i = 0; i < NST; i++) { mbar_init(BAR(Y_FULL + i), 1); mbar_init(BAR(Y_EMPTY + i), 4 * ARV); }
         for (int b = 0; b < 2; b++) {
             /* (SRCNN_PI: the operand-written half of the merged barriers is a bar.sync inside the producer group; only the
              * four drainer warps arrive here) */
             constexpr int e1w = SRCNN_E1_SPLIT ? 8 : 4;               /* epilogue I warps working on one row */
-            mbar_init(BAR(A1_FULL + b), ARV * (SRCNN_E1IM ? 4 : (SRCNN_MERGE_BAR && !SRCNN_PI) ? 4 + e1w : (SRCNN_PI ? e1w : 4))); mbar_init(BAR(M1_DONE + b), 1);
+            mbar_init(BAR(A1_FULL + b), ARV * ((SRCNN_MERGE_BAR && !SRCNN_PI) ? 4 + e1w : (SRCNN_PI ? e1w : 4))); mbar_init(BAR(M1_DONE + b), 1);
             mbar_init(BAR(D1_EMPTY_ + b), ARV * e1w);
             mbar_init(BAR(A2_FULL + b), ARV * ((SRCNN_MERGE_BAR && !SRCNN_PI) ? e1w + 4 : (SRCNN_PI ? 4 : e1w))); mbar_init(BAR(M2_DONE + b), 1);
             mbar_init(BAR(D2_EMPTY_ + b), ARV * 4);
         }
-        if (NB1 == 3) { mbar_init(BAR(A1_FULL + 2), ARV * 8); mbar_init(BAR(M1_DONE + 2), 1); mbar_init(BAR(D1_EMPTY_ + 2), ARV * 4); }
         for (int j = 0; j < 4; j++) { mbar_init(BAR(A3_FULL + j), 4 * ARV); mbar_init(BAR(A3_EMPTY + j), 1); }
         for (int b = 0; b < 2; b++) { mbar_init(BAR(M3_DONE + b), 1); mbar_init(BAR(D3_EMPTY + b), 4 * ARV); mbar_init(BAR(A1_FREE + b), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -640,29 +566,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             const uint32_t db0 = (uint32_t)umma_desc(sW, 128, (K1 / 8) * 128);
             constexpr uint32_t dh1 = umma_desc_hi((K1 / 8) * 128);
             uint32_t pr = 0;                                               /* global row-pair counter */
-#if SRCNN_TRIPLE
-            uint32_t b3 = 0, ph3 = 0;
-            for (int u = 0; u < span.nunits; u++) {
-                const Unit un = unit_of(p, span, u);
-                uint32_t R = (uint32_t)(un.ra % 9);
-                #pragma unroll 1
-                for (int n = 0; n < un.nrows; n++) {
-                    WAITS(0, 0, BAR(A1_FULL) + 8u * b3, ph3);
-                    tc_fence_after();
-                    if (ISSUE_LANE()) {
-                        const uint32_t db = db0 + R * (B1_BYTES >> 4);
-                        #pragma unroll
-                        for (int s = 0; s < K1 / 16; s++)
-                            umma_ts(tmem + D1_COL + b3 * D1_STR, tmem + A1_COL + b3 * A1_STR + 8 * s, db + 16 * s, dh1, umma_idesc(N1), s > 0);
-                        umma_commit(BAR(M1_DONE) + 8u * b3);
-                    }
-                    ISSUE_SYNC();
-                    R = (R == NROT - 1) ? 0 : R + 1;
-                    if (++b3 == 3) { b3 = 0; ph3 ^= 1; }
-                }
-            }
-            (void)pr; (void)myb;
-#else
             for (int u = 0; u < span.nunits; u++) {
                 const Unit un = unit_of(p, span, u);
                 uint32_t R = (uint32_t)(un.ra % 9);   /* weight-image rotation of conv II row q: (q + 2) mod 9 */
@@ -692,9 +595,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
 #else
                             #pragma unroll
                             for (int s = 0; s < K1 / 16; s++) {
-#ifdef SRCNN_DIAG_M1TWO
-                                if (s > 1) continue;
-#endif
                                 umma_ts(tmem + D1_COL + b * D1_STR, tmem + A1_COL + b * A1_STR + 8 * s, db + 16 * s, dh1, umma_idesc(N1), s > 0);
                             }
 #endif
@@ -709,7 +609,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     }
                 }
             }
-#endif
             ISSUER_END
         } else if (warp == W_MMA2 || warp == W_MMA2B) {
             const uint32_t myb = warp == W_MMA2B;
@@ -718,12 +617,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             const uint32_t dbb = (uint32_t)umma_desc(sW + W_B2B, 128, 256);
             constexpr uint32_t dh2 = umma_desc_hi((K2 / 8) * 128), dhb = umma_desc_hi(256);
             const int total = total_rows(p, span);
-            uint32_t r3 = 0;                                               /* SRCNN_TRIPLE: row mod 3 = conv I operand buffer (bias inputs) */
             #pragma unroll 1
             for (int g = 0; g < total; g += 2) {
                 const uint32_t ph = (g >> 1) & 1;
                 #pragma unroll
-                for (uint32_t b = 0; b < 2; b++, r3 = (r3 == 2 ? 0 : r3 + 1)) {
+                for (uint32_t b = 0; b < 2; b++) {
                     if (SRCNN_ISSUE_SPLIT && b != myb) continue;
                     if (ISSUE_LANE()) TLI(23, g + b);
                     WAITS(4, 0, BAR(A2_FULL + b), ph);
@@ -731,15 +629,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     tc_fence_after();
                     if (ISSUE_LANE()) {
                         TLI(9, g + b);
-#ifdef SRCNN_DIAG_M2ONE
-                        umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR, db, dh2, umma_idesc(N2), 0);
-#else
                         #pragma unroll
                         for (int s = 0; s < K2 / 16; s++)
                             umma_ts(tmem + D2_COL + b * D2_STR, tmem + A2_COL + b * A2_STR + 8 * s, db + 16 * s, dh2, umma_idesc(N2), s > 0);
                         if (!SRCNN_BIAS2_EPI)
-                            umma_ts(tmem + D2_COL + b * D2_STR, tmem + A1_COL + (SRCNN_TRIPLE ? r3 : b) * A1_STR + ABIAS_OFF, dbb, dhb, umma_idesc(N2), 1);     /* + bias */
-#endif
+                            umma_ts(tmem + D2_COL + b * D2_STR, tmem + A1_COL + b * A1_STR + ABIAS_OFF, dbb, dhb, umma_idesc(N2), 1);     /* + bias */
                         umma_commit(BAR(M2_DONE + b));
                         TLI(10, g + b);
                     }
@@ -770,9 +664,7 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                     if (ISSUE_LANE()) TLI(24, 2 * sg + 4);
                     WAITS(8, 0, BAR(A3_FULL) + 8u * (kn & 3), (kn >> 2) & 1);
                     if (ISSUE_LANE()) TLI(14, 2 * sg + 4);
-#ifndef SRCNN_DIAG_NOD3WAIT
                     WAITS(9, 1, BAR(D3_EMPTY + (sg & 1)), ((sg >> 1) & 1) ^ 1);
-#endif
                     tc_fence_after();
                     if (ISSUE_LANE()) {
                         TLI(15, 2 * sg + 4);
@@ -788,9 +680,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                                 const uint32_t pa = tmem + A3_COL + ((kp + j) & 3u) * (2 * A3_SLOT);
                                 #pragma unroll
                                 for (int h = 0; h < 4; h++) {
-#ifdef SRCNN_DIAG_M3ONE
-                                    if ((j | h) > 0) continue;
-#endif
                                     umma_ts(d3, pa + 8 * h, db3 + (uint32_t)((4 * j + h) * (B3_TILE >> 4)), dh3, umma_idesc(N3), (j | h) > 0);
                                 }
                                 TLI(26 + j, 2 * sg + 4);
@@ -821,73 +710,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
             }
             ISSUER_END
         }
-#if SRCNN_E1IM
-    } else if (warp >= W_IM2COL && warp < W_IM2COL + 4) {
-        reg_dec<24>();                      /* (idle: its registers go to the epilogue I groups) */
-    } else if (warp >= W_E1 && warp < W_E1 + 8) {
-        /* ===================== epilogue I + operand rewrite (two groups, one per row parity) ================== */
-        reg_inc<120>();
-        const uint32_t b = (uint32_t)(warp - W_E1) >> 2;
-        const int t = ((warp - W_E1) & 3) * 32 + lane;
-        const uint32_t d1 = lane_base + D1_COL + b * D1_STR, a2 = lane_base + A2_COL + b * A2_STR, a1 = lane_base + A1_COL + b * A1_STR;
-        const int total = total_rows(p, span);
-        /* cursor over the rows of this parity whose operand is written next: unit nu, row nn (nn = b, b+2, ...); everything the
-         * cursor needs lives in plain scalars (the helpers are force-inlined: no closure object in local memory) */
-        E1Cur cu;
-        cu.nu = 0; cu.nn = (int)b; cu.ckbase = 0; cu.got = 0; cu.rel = 0; cu.nrows = 0; cu.ra9 = 0; cu.woff = 0; cu.sh = 0;
-        if (span.nunits > 0) e1_enter(cu, unit_of(p, span, 0), sY, t);
-        if (total > 0) {
-            /* prologue: the operand of this parity's first row; D1[b] starts out drained */
-            e1_write_full(cu, bar0, a1);
-            tmem_wait_st();
-            tc_fence_before();
-            warp_arrive(BAR(A1_FULL) + 8u * b, lane);
-            e1_advance(cu, p, span, bar0, sY, t, (int)b, lane);
-        }
-        #pragma unroll 1
-        for (int g = 0; g < total; g += 2) {
-            const uint32_t ph = (g >> 1) & 1;
-            const bool more = cu.nu < span.nunits;                     /* an operand is still to be written (row g + 2 of this parity) */
-            const bool full = more && cu.nn < 2;
-            uint32_t wa[5], wb[5];
-            uint32_t sa = 0;
-            if (more && !full) {                                       /* the two new plane rows, fetched before the wait */
-                e1_ldrow(cu, bar0, cu.nn + 7, wa); e1_ldrow(cu, bar0, cu.nn + 8, wb);
-                sa = (uint32_t)(cu.ra9 + cu.nn + 7) % 9u;
-            }
-            WAITP(0, BAR(M1_DONE) + 8u * b, ph);
-            tc_fence_after();
-            uint32_t v[64];
-            if (!full) { tmem_ld32(d1, v); tmem_ld32(d1 + 32, v + 32); }
-            if (more) {
-                if (full) { e1_write_full(cu, bar0, a1); tmem_ld32(d1, v); tmem_ld32(d1 + 32, v + 32); }
-                else if (sa != 8u) {                                   /* ten adjacent columns */
-                    tmem_st4(a1 + 5 * sa, wa[0], wa[1], wa[2], wa[3]);
-                    tmem_st2(a1 + 5 * sa + 4, wa[4], wb[0]);
-                    tmem_st4(a1 + 5 * sa + 6, wb[1], wb[2], wb[3], wb[4]);
-                } else {                                               /* slots 8 and 0 */
-                    tmem_st4(a1 + 40, wa[0], wa[1], wa[2], wa[3]);
-                    tmem_st1(a1 + 44, wa[4]);
-                    tmem_st4(a1, wb[0], wb[1], wb[2], wb[3]);
-                    tmem_st1(a1 + 4, wb[4]);
-                }
-                tmem_wait_st();
-            }
-            tmem_wait_ld();
-            tc_fence_before();
-            warp_arrive(BAR(A1_FULL) + 8u * b, lane);                  /* operand of row g + 2 written, accumulator of row g drained */
-            #pragma unroll
-            for (int m = 0; m < 32; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
-            WAITP(1, BAR(M2_DONE) + 8u * b, ph ^ 1);                   /* MMA2 of the previous row of this parity has consumed A2[b] */
-            tc_fence_after();
-            tmem_st16(a2, v);
-            tmem_st16(a2 + 16, v + 16);
-            tmem_wait_st();
-            tc_fence_before();
-            warp_arrive(BAR(A2_FULL) + 8u * b, lane);
-            if (more) e1_advance(cu, p, span, bar0, sY, t, (int)b, lane);       /* (off the hand-over paths) */
-        }
-#else
     } else if (warp >= W_IM2COL && warp < W_IM2COL + 4) {
         /* ===================== im2col: smem Y16 ring -> 9-slot register ring -> A1 in TMEM ==================== */
         reg_inc<96>();
@@ -908,16 +730,11 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 const uint32_t c = ck + (uint32_t)(rho / CH_ROWS), s = c % NST;
                 if ((rho % CH_ROWS) == 0) GWAITP(lead, NB_IM, 0, BAR(Y_FULL + s), (c / NST) & 1);
                 const uint32_t a = woff + s * CH_BYTES + (uint32_t)(rho % CH_ROWS) * (BOX_W * 2);
-#ifdef SRCNN_DIAG_NOFETCH      /* timing diagnosis only (wrong results): how much of the row period is im2col's fetch? */
-                #pragma unroll
-                for (int j = 0; j < 5; j++) w5[j] = a + j;
-#else
                 uint32_t x[6];
                 #pragma unroll
                 for (int j = 0; j < 6; j++) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[j]) : "r"(a + 4u * j));
                 #pragma unroll
                 for (int j = 0; j < 5; j++) w5[j] = __funnelshift_r(x[j], x[j + 1], sh);
-#endif
                 if ((rho % CH_ROWS) == CH_ROWS - 1 || rho == last_rho) warp_arrive(BAR(Y_EMPTY + s), lane);
             };
             /* Y row y always lives in slot (y + 6) mod 9, i.e. the k position of a tap depends on the absolute image row only
@@ -929,25 +746,19 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 constexpr int R = decltype(RC)::value;
                 fetch(n + 8, W[(R + 8) % 9]);
                 if (n < 0) return;
-#if SRCNN_TRIPLE
-                const uint32_t b = it % 3u, ph = (it / 3u) & 1;
-#else
                 const uint32_t b = it & 1, ph = (it >> 1) & 1;
-#endif
                 TL(0, it, t == 0);
 #if SRCNN_A1_EARLY && SRCNN_A1_PARTIAL && !SRCNN_PI
                 /* partial rewrite: only the K-steps that read the two oldest window rows of row it-2 must have run */
                 WAITS(2, 1, BAR(A1_FREE) + 8u * b, ph ^ 1);
                 if (n < 2) WAITS(2, 1, BAR(M1_DONE) + 8u * b, ph ^ 1);     /* whole operand rewritten: all of row it-2's MMAs */
 #else
-#ifndef SRCNN_DIAG_NOA1WAIT    /* timing diagnosis only (races): the operand side leaves conv I's reuse cycle altogether */
                 GWAITS(lead, NB_IM, 2, 1, BAR(M1_DONE) + 8u * b, ph ^ 1);         /* MMA1 of row it-2 has consumed A1[b] */
-#endif
 #endif
                 tc_fence_after();
                 TL(1, it, t == 0);
                 const uint32_t dst = lane_base + A1_COL + b * A1_STR;
-                if (!SRCNN_A1_PARTIAL || n < NB1) {
+                if (!SRCNN_A1_PARTIAL || n < 2) {
                     /* first two rows of a unit: the whole operand (both parity buffers still hold another unit's rows) */
                     uint32_t r[16];
                     #pragma unroll
@@ -964,20 +775,9 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 } else {
                     /* A1[b] still holds the operand of row n-2, and the slot -> column map never moves: only the two ring
                      * slots refilled since then (Y rows n+7 and n+8) differ -- 10 of the 48 columns */
-#if SRCNN_TRIPLE
-                    {   /* three ring slots changed since the same-buffer row three rows earlier */
-                        constexpr int SZ = (R + 6) % 9;
-                        tmem_st4(dst + 5 * SZ, W[SZ][0], W[SZ][1], W[SZ][2], W[SZ][3]);
-                        tmem_st1(dst + 5 * SZ + 4, W[SZ][4]);
-                    }
-#endif
                     constexpr int SA = (R + 7) % 9, SB = (R + 8) % 9;
                     const uint32_t (&wa)[5] = W[SA];
                     const uint32_t (&wb)[5] = W[SB];
-#ifdef SRCNN_DIAG_NOST      /* timing diagnosis only (wrong results): the A1 rewrite leaves the M1 -> M1 cycle */
-                    if (wa[0] == 0x12345678u && wb[4] == 0x9abcdef0u)
-#endif
-                    {
                     tmem_st4(dst + 5 * SA, wa[0], wa[1], wa[2], wa[3]);
                     if (SB == SA + 1) {
                         tmem_st2(dst + 5 * SA + 4, wa[4], wb[0]);
@@ -986,7 +786,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                         tmem_st1(dst + 5 * SA + 4, wa[4]);
                         tmem_st4(dst + 5 * SB, wb[0], wb[1], wb[2], wb[3]);
                         tmem_st1(dst + 5 * SB + 4, wb[4]);
-                    }
                     }
                 }
                 tmem_wait_st();
@@ -1056,54 +855,30 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
         const uint32_t b = (uint32_t)(warp - W_E1) >> 2;
         const bool lead = (uint32_t)(warp & 3) == ((SRCNN_LEADS >> (4 + 4 * b)) & 15u);
         const int total = total_rows(p, span);
-#if !SRCNN_TRIPLE
         const uint32_t d1 = lane_base + D1_COL + b * D1_STR;
-#endif
         const uint32_t a2 = lane_base + A2_COL + b * A2_STR;
 #if SRCNN_PI
         const uint32_t db2 = (uint32_t)umma_desc(sW + W_B2, 128, (K2 / 8) * 128);
         const uint32_t dbb2 = (uint32_t)umma_desc(sW + W_B2B, 128, 256);
         constexpr uint32_t dh2 = umma_desc_hi((K2 / 8) * 128), dhb2 = umma_desc_hi(256);
 #endif
-#if SRCNN_TRIPLE
-        if (total > 0) { warp_arrive(BAR(D1_EMPTY) + 8u * b, lane); if (b == 0) warp_arrive(BAR(D1_EMPTY) + 8u * 2, lane); }
-        uint32_t b3 = b, ph3 = 0;                                        /* buffer and phase of this group's current row g + b */
-#else
         if (SRCNN_MERGE_BAR && total > 0) warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);     /* D1[b] starts out drained */
-#endif
         #pragma unroll 1
         for (int g = 0; g < total; g += 2) {
             const uint32_t ph = (g >> 1) & 1;
             uint32_t v[64];
-#if SRCNN_TRIPLE
-            const uint32_t d1 = lane_base + D1_COL + b3 * D1_STR;
-            const uint32_t bar1 = BAR(M1_DONE) + 8u * b3, bare = BAR(D1_EMPTY) + 8u * b3;
-            GWAITS(lead, NB_E1 + b, 3, 0, bar1, ph3);
-            b3 += 2; if (b3 >= 3) { b3 -= 3; ph3 ^= 1; }
-#else
-            const uint32_t bare = BAR(D1_EMPTY) + 8u * b;
             GWAITS(lead, NB_E1 + b, 3, 0, BAR(M1_DONE) + 8u * b, ph);
-#endif
             tc_fence_after();
             TL(5, g + b, ((warp & 3) | lane) == 0);
-#ifdef SRCNN_DIAG_D1EARLY   /* timing diagnosis only (races): the D1 drain leaves the M1 -> M1 cycle */
-            warp_arrive(bare, lane);
-#endif
             tmem_ld32(d1, v);
             tmem_ld32(d1 + 32, v + 32);
             tmem_wait_ld();
             tc_fence_before();
             TL(6, g + b, ((warp & 3) | lane) == 0);
-#ifndef SRCNN_DIAG_D1EARLY
-            warp_arrive(bare, lane);
-#endif
-#ifndef SRCNN_DIAG_E1NOCVT
+            warp_arrive(BAR(D1_EMPTY) + 8u * b, lane);
             #pragma unroll
             for (int m = 0; m < 32; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
-#endif
-#ifndef SRCNN_DIAG_NOM2WAIT
             GWAITS(lead, NB_E1 + b, 6, 1, BAR(M2_DONE) + 8u * b, ph ^ 1);              /* MMA2 of the previous row of this parity has consumed A2[b] */
-#endif
             tc_fence_after();
             TL(7, g + b, ((warp & 3) | lane) == 0);
             tmem_st16(a2, v);
@@ -1133,7 +908,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
 #endif
         }
 #endif
-#endif   /* SRCNN_E1IM */
     } else if (warp >= W_E2 && warp < W_E2 + 4) {
         /* ===================== epilogue II: D2 (bias included) -> ReLU -> FP16 -> A3 ring ===================== */
 #if SRCNN_E2_DECOUPLE
@@ -1197,14 +971,10 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                         #pragma unroll
                         for (int m = 0; m < 32; m++) v[m] = __float_as_uint(__fadd_rn(__uint_as_float(v[m]), cBias2[m]));
                     }
-#ifndef SRCNN_DIAG_E2NOCVT
                     #pragma unroll
                     for (int m = 0; m < 16; m++) v[m] = cvt_relu_h2(v[2 * m], v[2 * m + 1]);
-#endif
                     if (b == 0) {
-#ifndef SRCNN_DIAG_NOA3WAIT     /* timing diagnosis only (races): is the conv III operand ring's reuse cycle the binding one? */
                         GWAITP(lead, NB_E2, 1, BAR(A3_EMPTY) + 8u * js, ((kg >> 2) & 1) ^ 1);   /* every set that read this pair slot is done */
-#endif
                         tc_fence_after();
                     }
                     tmem_st16(a3 + b * A3_SLOT, v);
@@ -1318,9 +1088,6 @@ conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap ymap)
                 tc_fence_before();
                 TL(18, 2 * sg + 4, t == 0);
                 warp_arrive(BAR(D3_EMPTY + (sg & 1)), lane);
-#ifdef SRCNN_DIAG_NOGATHER     /* timing diagnosis only (no output) */
-                if (z[0] != 0x12345678u) continue;
-#endif
                 const uint32_t poff = (sg & 1) * (10 * 128 * 4);            /* exchange buffer of this set */
                 const uint32_t pdst = pst + poff;
                 #pragma unroll
