@@ -338,7 +338,7 @@ __device__ __forceinline__ bool elect_one()
 /* SRCNN_ARRIVE_ALL = 1: every lane arrives for itself (barrier counts x 32): no __syncwarp and no predicated single-lane
  * arrive on the hand-over path */
 #ifndef SRCNN_ARRIVE_ALL
-#define SRCNN_ARRIVE_ALL 0
+#define SRCNN_ARRIVE_ALL 1      /* measured (round 2, three interleaved runs each): 0.1333-0.1337 vs 0.1341-0.1344 ms */
 #endif
 constexpr uint32_t ARV = SRCNN_ARRIVE_ALL ? 32u : 1u;      /* arrivals per warp */
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane)
