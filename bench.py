@@ -182,10 +182,16 @@ def cpu_baseline_leg(name, ctx, budget_s=25.0):
             par["conv_max_abs_lsb"] = int(dc.max()); ok = ok and bool(dc.max() <= 1)
         # the interpolated Y plane of the product route (FP32 copy written on request) against the reference's resize: 1e-5 relative
         try:
+            import torch                                     # (one device-resident pass over the whole frame: a host pass is cut
+            d_src = torch.from_numpy(img).cuda()             #  into sub-strips, and the plane getters describe the last one)
+            d_out = torch.empty((oh, ow, d), dtype=torch.uint8, device="cuda")
             ctx.set_keep_planes(2)
-            ctx.pass_host(img, m, filt, False)
-            _, gy = ctx.get_plane(0, (oh, ow))
+            ctx.pass_device(d_src.data_ptr(), w, h, d, m, filt, d_out.data_ptr(), 0)
+            ctx.sync()
+            r0, gy = ctx.get_plane(0, (oh, ow))
             ctx.set_keep_planes(False)
+            if r0 != 0 or gy.shape != (oh, ow):
+                raise RuntimeError("plane getter returned rows from %d, shape %r" % (r0, gy.shape))
             ry = orc.resize(orc.color_in(img)[0], ow, oh, filt)
             rel = float((np.abs(gy - ry) / np.maximum(np.abs(ry), 1.0)).max())
             par["y_plane_rel_max"] = rel; par["y_plane_differing_samples"] = int((gy != ry).sum())

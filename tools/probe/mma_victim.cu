@@ -76,6 +76,29 @@ __global__ void __launch_bounds__(256) k(long long* out, uint32_t* sink)
             for (int o = 16; o; o >>= 1) { x = max(x, __shfl_xor_sync(~0u, x, o)); y = max(y, __shfl_xor_sync(~0u, y, o)); }
             if (lane == 0 && blockIdx.x == 0) { out[16 + 3 * b] = x - c0; out[17 + 3 * b] = y - c0; out[18 + 3 * b] = cc[b] - c0; }
         }
+    } else if (warp == 1 && IM == 6) {
+        /* the conv kernel's issuer loop: per batch  if (elect) { 6 MMAs; commit; stamp }  __syncwarp();  stamp */
+        long long ca[8], cb[8], cc[8];
+        const long long c0 = clock64();
+        #pragma unroll
+        for (int b = 0; b < 8; b++) {
+            ca[b] = cb[b] = 0;
+            if (elect_one()) {
+                const uint64_t dbb = make_desc(smem_u32(sB) + ((sdat[b] & 1) << 4), 128, 256);
+                ca[b] = clock64();
+                #pragma unroll
+                for (int s = 0; s < 6; s++) mma(tmem + (b & 1) * 64, tmem + 480, dbb + 16 * (s & 3), idesc, s > 0);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar) + 8 * (b + 1)) : "memory");
+                cb[b] = clock64();
+            }
+            cc[b] = clock64();
+        }
+        mbar_wait(smem_u32(&bar) + 8 * 8, 0);
+        for (int b = 0; b < 8; b++) {
+            long long x = ca[b], y = cb[b];
+            for (int o = 16; o; o >>= 1) { x = max(x, __shfl_xor_sync(~0u, x, o)); y = max(y, __shfl_xor_sync(~0u, y, o)); }
+            if (lane == 0 && blockIdx.x == 0) { out[16 + 3 * b] = x - c0; out[17 + 3 * b] = y - c0; out[18 + 3 * b] = cc[b] - c0; }
+        }
     } else if (warp == 1) {
         if (elect_one()) {
             if (IM == 3) {
@@ -166,7 +189,11 @@ template <int IM, int VW> void run(long long* d, uint32_t* sink)
     k<IM, VW><<<148, 256>>>(d, sink);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[48]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    if (IM == 5) {
+    if (IM == 6) {
+        printf("the same WITHOUT the explicit __syncwarp: per batch [start, after commit, after the if]:");
+        for (int b = 0; b < 8; b++) printf(" [%lld %lld %lld]", h[16 + 3 * b], h[17 + 3 * b], h[18 + 3 * b]);
+        printf("  (%s)\n", cudaGetErrorString(e));
+    } else if (IM == 5) {
         printf("issuer loop as in conv_tc (elect / 6 MMAs + commit / __syncwarp): per batch [start, after commit, after __syncwarp]:");
         for (int b = 0; b < 8; b++) printf(" [%lld %lld %lld]", h[16 + 3 * b], h[17 + 3 * b], h[18 + 3 * b]);
         printf("  (%s)\n", cudaGetErrorString(e));
@@ -188,6 +215,7 @@ int main()
     run<3, 0>(d, sink);
     run<4, 0>(d, sink);
     run<5, 0>(d, sink);
+    run<6, 0>(d, sink);
     run<0, 0>(d, sink); run<1, 0>(d, sink); run<2, 0>(d, sink);
     run<0, 1>(d, sink); run<1, 1>(d, sink); run<2, 1>(d, sink);
     run<0, 2>(d, sink); run<1, 2>(d, sink); run<2, 2>(d, sink);
