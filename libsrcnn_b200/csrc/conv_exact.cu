@@ -163,24 +163,27 @@ conv_exact_kernel(const float* __restrict__ y, int dw, int dh, int win_row0, int
     out[(size_t)(orow - row0) * dw + ocol] = t;
 }
 
-void launch_conv_exact(const float* y, unsigned dw, unsigned dh, unsigned win_row0, unsigned win_rows,
-                       float* out, unsigned row0, unsigned row1, cudaStream_t s)
+/* -> 0, or the CUDA error of the one-time per-device set-up (weights copy, shared-memory opt-in); launch errors surface through
+ * cudaGetLastError like those of every other kernel */
+int launch_conv_exact(const float* y, unsigned dw, unsigned dh, unsigned win_row0, unsigned win_rows,
+                      float* out, unsigned row0, unsigned row1, cudaStream_t s)
 {
     /* the opt-in and the global copy of the conv I / II weights are per device: set up once per device, not on every launch */
     static std::atomic<bool> configured[64];
     static float* d_w[64];
     static std::mutex mu;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
     if (!configured[dev].load(std::memory_order_acquire)) {
         std::lock_guard<std::mutex> lock(mu);
         if (!configured[dev].load(std::memory_order_relaxed)) {
             float* w = nullptr;
-            if (cudaMalloc(&w, (81 * 64 + 64 * 32) * sizeof(float)) != cudaSuccess) return;
-            if (cudaMemcpy(w, SRCNN_W1, sizeof(SRCNN_W1), cudaMemcpyHostToDevice) != cudaSuccess ||
-                cudaMemcpy(w + 81 * 64, SRCNN_W2, sizeof(SRCNN_W2), cudaMemcpyHostToDevice) != cudaSuccess ||
-                cudaFuncSetAttribute(conv_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXACT_SMEM) != cudaSuccess) {
-                cudaFree(w); return;
+            cudaError_t e = cudaMalloc(&w, (81 * 64 + 64 * 32) * sizeof(float));
+            if (e != cudaSuccess) return (int)e;
+            if ((e = cudaMemcpy(w, SRCNN_W1, sizeof(SRCNN_W1), cudaMemcpyHostToDevice)) != cudaSuccess ||
+                (e = cudaMemcpy(w + 81 * 64, SRCNN_W2, sizeof(SRCNN_W2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+                (e = cudaFuncSetAttribute(conv_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXACT_SMEM)) != cudaSuccess) {
+                cudaFree(w); return (int)e;
             }
             d_w[dev] = w;
             configured[dev].store(true, std::memory_order_release);
@@ -189,6 +192,7 @@ void launch_conv_exact(const float* y, unsigned dw, unsigned dh, unsigned win_ro
     dim3 grid((dw + TW_ - 1) / TW_, (row1 - row0 + TH_ - 1) / TH_);
     conv_exact_kernel<<<grid, NTHR, EXACT_SMEM, s>>>(y, (int)dw, (int)dh, (int)win_row0, (int)(win_row0 + win_rows), out, (int)row0, (int)row1,
                                                       d_w[dev], d_w[dev] + 81 * 64);
+    return 0;
 }
 
 } // namespace srcnn

@@ -122,7 +122,7 @@ void launch_pack_y16(const float* y, unsigned dw, unsigned dh, unsigned win_row0
 
 /* fused conv I+II+III, bit-exact FP32 CUDA-core path (validation mode).
  * y: window rows [win_row0, ...) of the dw x dh interpolated plane; out: rows [row0,row1) x dw */
-void launch_conv_exact(const float* y, unsigned dw, unsigned dh, unsigned win_row0, unsigned win_rows,
+int launch_conv_exact(const float* y, unsigned dw, unsigned dh, unsigned win_row0, unsigned win_rows,
                        float* out, unsigned row0, unsigned row1, cudaStream_t s);
 int  conv_exact_init();    /* current device: uploads the FP32 parameter tables to __constant__ memory, opts the kernel in to its
                               dynamic shared memory size */

@@ -503,7 +503,11 @@ int run_pass(srcnn_b200_ctx* ctx, Plan& p, const uint8_t* d_src_base, long src_b
         }
         ctx->launches++;
     } else {
-        launch_conv_exact(P_dst, p.ow, p.oh, p.e0, erows, Yp, p.r0, p.r1, s); ctx->launches++;
+        if (const int ce = launch_conv_exact(P_dst, p.ow, p.oh, p.e0, erows, Yp, p.r0, p.r1, s)) {
+            ctx->err = std::string("conv_exact set-up: ") + cudaGetErrorString((cudaError_t)ce);
+            return SRCNN_B200_ECUDA;
+        }
+        ctx->launches++;
         ctx->last_has_yp = true;
     }
     st.mark();
@@ -1366,7 +1370,11 @@ int srcnn_b200_stage_conv(srcnn_b200_ctx* ctx, const float* y, unsigned w, unsig
     cudaStream_t s = ctx->stream;
     CK(cudaMemcpyAsync(Y, y, n * sizeof(float), cudaMemcpyHostToDevice, s));
     if (mode == SRCNN_B200_CONV_EXACT) {
-        launch_conv_exact(Y, w, h, 0, h, O, 0, h, s); ctx->launches++;
+        if (const int ce = launch_conv_exact(Y, w, h, 0, h, O, 0, h, s)) {
+            ctx->err = std::string("conv_exact set-up: ") + cudaGetErrorString((cudaError_t)ce);
+            return SRCNN_B200_ECUDA;
+        }
+        ctx->launches++;
     } else if (mode == SRCNN_B200_CONV_TENSOR) {
         const Y16Geom g = y16_geometry(w, h);
         CK(ctx->y16.ensure((size_t)g.pitch * g.rows * sizeof(__half)));
