@@ -8,9 +8,9 @@
  *             coordinates), per input channel a double partial over 25 taps of float products, float running sum
  *             over channels, + bias, clamp to [0,255]
  *
- * One CTA produces a 16x16 output tile: conv I/II are evaluated at the 20x20 in-image positions conv III needs
- * (the 64- and 32-channel intermediates live in registers / shared memory only), then conv III reads the tile
- * with the reference's coordinate clamping.
+ * One 512-thread CTA produces a 28x12 output tile: conv I/II are evaluated at the 32x16 in-image positions conv III needs, one
+ * position per thread (the 64- and 32-channel intermediates live in registers / shared memory only), then conv III reads the
+ * tile with the reference's coordinate clamping.  Conv I / II weights are staged in shared memory (see below).
  */
 #include "kernels.h"
 #include <atomic>
@@ -19,9 +19,7 @@
 
 namespace srcnn {
 
-__constant__ float cW1[81][64];
 __constant__ float cB1[64];
-__constant__ float cW2[64][32];
 __constant__ float cB2[32];
 __constant__ float cW3[25][32];
 __constant__ float cB3;
@@ -29,9 +27,7 @@ __constant__ float cB3;
 int conv_exact_init()
 {
     cudaError_t e;
-    if ((e = cudaMemcpyToSymbol(cW1, SRCNN_W1, sizeof(SRCNN_W1))) != cudaSuccess) return (int)e;
     if ((e = cudaMemcpyToSymbol(cB1, SRCNN_B1, sizeof(SRCNN_B1))) != cudaSuccess) return (int)e;
-    if ((e = cudaMemcpyToSymbol(cW2, SRCNN_W2, sizeof(SRCNN_W2))) != cudaSuccess) return (int)e;
     if ((e = cudaMemcpyToSymbol(cB2, SRCNN_B2, sizeof(SRCNN_B2))) != cudaSuccess) return (int)e;
     if ((e = cudaMemcpyToSymbol(cW3, SRCNN_W3, sizeof(SRCNN_W3))) != cudaSuccess) return (int)e;
     if ((e = cudaMemcpyToSymbol(cB3, &SRCNN_B3, sizeof(float))) != cudaSuccess) return (int)e;
